@@ -1,0 +1,580 @@
+// libcvmx: C ABI (include/cvmx.h) over the sm_100a kernels.  Host-side orchestration only; all
+// arithmetic of the hot path runs in kernels_stats.cuh / kernels_gram.cuh.  There is no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cvmx.h"
+#include "kernels_gram.cuh"
+#include "kernels_stats.cuh"
+
+using namespace cvmx;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct Plan {                 // launch plan of one fold range (cached)
+  int64_t fold_begin = -1, fold_end = -1; uint32_t want = 0; int64_t csr_version = -1;
+  std::vector<GramUnit> units;
+  std::vector<int2> tiles;
+  std::vector<int32_t> fold_units;   // first unit of each fold
+  std::vector<int32_t> split_folds;  // folds with nsplit > 1
+  int64_t n_partial_units = 0;
+  int64_t max_rows = 0;
+};
+
+}  // namespace
+
+struct cvmx_handle {
+  int device = 0, dtype = CVMX_F64;
+  uint32_t flags = 0;
+  int64_t ddof = 1;
+  double resolution = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  // fitted state
+  bool fitted = false, weighted = false;
+  int64_t N = 0, K = 0, M = 0, ld = 0;
+  DevBuf Z, w, Ttot, sum_z, sumsq_z, fit_scal;
+  // CSR (device) + host offsets
+  int64_t P = 0, csr_version = 0;
+  DevBuf d_off, d_idx;
+  std::vector<int64_t> h_off;
+  // ad-hoc index set (cvmx_training_indices)
+  DevBuf a_off, a_idx;
+  // scratch
+  DevBuf units, tiles, fold_units, split_folds, partials, stats, fscal, pwcols, errflag, out_xx, out_xy, out_small;
+  Plan plan;
+  bool attr_gram = false, attr_mom = false;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int32_t fail(cvmx_t* h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+
+#define CU(h, expr)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? CVMX_ERR_NOMEM : CVMX_ERR_CUDA,                  \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
+  } while (0)
+
+inline size_t esz(const cvmx_t* h) { return h->dtype == CVMX_F64 ? 8 : 4; }
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- launch planning -------------------------------------------------------------------------------
+// Tiles on or above the diagonal of the K x (K+M) result, restricted to what `want` needs.
+void plan_tiles(const cvmx_t* h, uint32_t want, std::vector<int2>& tiles) {
+  tiles.clear();
+  const int64_t TI = (h->K + GB - 1) / GB, TJ = (h->K + h->M + GB - 1) / GB;
+  for (int64_t bi = 0; bi < TI; ++bi)
+    for (int64_t bj = bi; bj < TJ; ++bj) {
+      const bool has_x = bj * GB < h->K;
+      const bool has_y = (bj + 1) * GB > h->K && h->M > 0;
+      if (((want & CVMX_WANT_XTX) && has_x) || ((want & CVMX_WANT_XTY) && has_y)) tiles.push_back(make_int2((int)bi, (int)bj));
+    }
+}
+
+// Row-split policy.  Many small folds: one unit per fold, epilogue fused into the Gram kernel.  Few large
+// folds: split the rows so that (units x tiles) fills the SMs in whole waves; partials are reduced in
+// split order by k_gram_reduce (deterministic).
+void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int ntiles, Plan& pl) {
+  const int64_t Pn = f1 - f0;
+  pl.units.clear(); pl.fold_units.assign(Pn, 0); pl.split_folds.clear();
+  pl.n_partial_units = 0; pl.max_rows = 0;
+  const int64_t sms = h->sm_count;
+  int64_t rows_per_unit = INT64_MAX;
+  if (Pn * ntiles < 8 * sms) {
+    double best = -1;
+    for (int64_t R = 2048; R <= 4096; R += GBK) {
+      int64_t items = 0;
+      for (int64_t f = f0; f < f1; ++f) items += std::max<int64_t>(1, (off[f + 1] - off[f] + R - 1) / R);
+      items *= ntiles;
+      const double eff = (double)items / (double)(sms * ((items + sms - 1) / sms));
+      if (eff > best + 1e-9) { best = eff; rows_per_unit = R; }
+    }
+  }
+  for (int64_t f = f0; f < f1; ++f) {
+    const int64_t beg = off[f], n = off[f + 1] - off[f];
+    pl.max_rows = std::max(pl.max_rows, n);
+    const int64_t ns = (rows_per_unit == INT64_MAX) ? 1 : std::max<int64_t>(1, (n + rows_per_unit - 1) / rows_per_unit);
+    pl.fold_units[f - f0] = (int32_t)pl.units.size();
+    if (ns > 1) pl.split_folds.push_back((int32_t)(f - f0));
+    // equal-sized splits, multiples of GBK rows
+    const int64_t per = round_up((n + ns - 1) / ns, GBK);
+    for (int64_t s = 0; s < ns; ++s) {
+      GramUnit u;
+      u.row_begin = beg + std::min(n, s * per);
+      u.row_end = beg + std::min(n, (s + 1) * per);
+      u.fold = (int32_t)(f - f0); u.split = (int32_t)s; u.nsplit = (int32_t)ns;
+      u.part_base = (int32_t)pl.n_partial_units;
+      pl.units.push_back(u);
+    }
+    if (ns > 1) pl.n_partial_units += ns;
+  }
+}
+
+template <typename T>
+int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const EpiParams<T>& epi) {
+  const int ntiles = (int)pl.tiles.size();
+  if (ntiles == 0 || pl.units.empty()) return CVMX_OK;
+  CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
+  CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
+  CU(h, h->fold_units.reserve(pl.fold_units.size() * sizeof(int32_t)));
+  CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  if (pl.n_partial_units) {
+    CU(h, h->partials.reserve((size_t)pl.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
+    CU(h, h->split_folds.reserve(pl.split_folds.size() * sizeof(int32_t)));
+    CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  }
+  GramParams<T> gp;
+  gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld;
+  gp.indices = d_indices;
+  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.partials = h->partials.as<double>();
+  gp.epi = epi;
+  const size_t smem = gram_smem_bytes<T>();
+  if (!h->attr_gram) {
+    CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(h, cudaFuncSetAttribute(k_gram_reduce<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->attr_gram = true;
+  }
+  const int64_t grid = (int64_t)pl.units.size() * ntiles;
+  if (grid > 0x7fffffffLL) return fail(h, CVMX_ERR_INVALID, "fold batch too large for one launch");
+  k_gram<T><<<(unsigned)grid, GTHREADS, smem, h->stream>>>(gp);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  if (!pl.split_folds.empty()) {
+    for (size_t s0 = 0; s0 < pl.split_folds.size(); s0 += 65535) {
+      const unsigned ny = (unsigned)std::min<size_t>(65535, pl.split_folds.size() - s0);
+      k_gram_reduce<T><<<dim3(ntiles, ny), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(),
+                                                                          h->split_folds.as<int32_t>() + s0);
+      h->launches++;
+    }
+    CU(h, cudaGetLastError());
+  }
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows) {
+  const size_t smem = moments_pipe_smem<T>();
+  if (!h->attr_mom) {
+    CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->attr_mom = true;
+  }
+  const bool pipe = max_rows >= 128;
+  for (int64_t f0 = 0; f0 < nfolds; f0 += 65535) {
+    const unsigned ny = (unsigned)std::min<int64_t>(65535, nfolds - f0);
+    MomentParams<T> q = mp;
+    if (mp.offsets) {
+      q.fold0 = mp.fold0 + f0;
+      q.fs = mp.fs + f0;
+      q.pw_cols = mp.pw_cols ? mp.pw_cols + f0 * 4 : nullptr;
+      q.stats = mp.stats + (size_t)f0 * 2 * mp.ld;
+    }
+    if (pipe) k_moments_pipe<T><<<dim3((unsigned)(mp.ld / MOM_COLS), ny), MOM_THREADS, smem, h->stream>>>(q);
+    else k_moments_direct<T><<<dim3((unsigned)((mp.ld + 127) / 128), ny), 128, 0, h->stream>>>(q);
+    h->launches++;
+  }
+  CU(h, cudaGetLastError());
+  return CVMX_OK;
+}
+
+template <typename T>
+__global__ void k_pack_scalars(const FoldScalars* __restrict__ fs, int64_t n, T* __restrict__ scal, int32_t* __restrict__ status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (scal) { scal[2 * i] = (T)fs[i].sw; scal[2 * i + 1] = (T)fs[i].nz; }
+  if (status) status[i] = fs[i].status;
+}
+
+// ---- fit -------------------------------------------------------------------------------------------
+template <typename T>
+int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M, int64_t ldy,
+                 const void* w, int32_t mem, int64_t g0, int64_t g1) {
+  const size_t sz = sizeof(T);
+  const int64_t ld = round_up(K + M, 32);
+  h->fitted = false;
+  h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = w != nullptr;
+  h->P = 0; h->csr_version++; h->plan = Plan();
+  CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
+  CU(h, h->w.reserve((size_t)std::max<int64_t>(N, 1) * sz));
+  CU(h, h->Ttot.reserve((size_t)K * ld * sz));
+  CU(h, h->sum_z.reserve(ld * sz));
+  CU(h, h->sumsq_z.reserve(ld * sz));
+  CU(h, h->fit_scal.reserve(sizeof(FitScalars)));
+  const cudaMemcpyKind kind = mem == CVMX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  T* Z = h->Z.as<T>();
+  if (N > 0) {
+    if (ld > K + M) CU(h, cudaMemset2DAsync(Z + (K + M), ld * sz, 0, (ld - K - M) * sz, N, h->stream));
+    CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
+    if (M > 0) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
+    if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
+    else { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
+  }
+  CU(h, cudaMemsetAsync(h->Ttot.p, 0, (size_t)K * ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->sum_z.p, 0, ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->sumsq_z.p, 0, ld * sz, h->stream));
+
+  CU(h, h->pwcols.reserve(4 * sz));
+  k_weight_mass<T><<<1, PW_THREADS, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
+                                                   h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
+  h->launches++;
+  CU(h, cudaGetLastError());
+
+  MomentParams<T> mp;
+  mp.Z = Z; mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
+  mp.offsets = nullptr; mp.indices = nullptr; mp.fold0 = 0; mp.N = N;
+  mp.flags = h->flags; mp.resolution = (T)h->resolution;
+  mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+  mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
+  int32_t rc = launch_moments<T>(h, mp, 1, N);
+  if (rc) return rc;
+
+  // totals: Gram over the row slab [g0, g1) with identity indexing, raw epilogue into Ttot
+  Plan pl;
+  plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), pl.tiles);
+  const int64_t off[2] = {g0, g1};
+  plan_units(h, off, 0, 1, (int)pl.tiles.size(), pl);
+  EpiParams<T> epi;
+  epi.mode = 0; epi.flags = 0; epi.want = CVMX_WANT_XTX | CVMX_WANT_XTY;
+  epi.K = K; epi.M = M; epi.ld = ld;
+  epi.Ttot = nullptr; epi.stats = nullptr; epi.fs = nullptr;
+  epi.out_xx = h->Ttot.as<T>(); epi.xx_pitch = ld; epi.xx_stride = 0;
+  epi.out_xy = h->Ttot.as<T>() + K; epi.xy_pitch = ld; epi.xy_stride = 0;
+  if (g1 > g0) {
+    rc = launch_gram<T>(h, pl, nullptr, epi);
+    if (rc) return rc;
+  }
+  FitScalars fsc;
+  CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (fsc.neg_weight) return fail(h, CVMX_ERR_NEG_WEIGHT, "Weights must be non-negative.");
+  h->fitted = true;
+  return CVMX_OK;
+}
+
+// ---- folds -----------------------------------------------------------------------------------------
+// Runs folds [f0, f1) of the CSR (d_off/d_idx on device, off on host) and leaves results in device
+// buffers: dxx [P'][K][K], dxy [P'][K][M] (either may be null per `want`), stats scratch, fscal scratch.
+template <typename T>
+int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const int64_t* off, int64_t f0, int64_t f1,
+                  uint32_t want, T* dxx, T* dxy, bool cacheable) {
+  const int64_t Pn = f1 - f0;
+  if (Pn <= 0) return CVMX_OK;
+  const size_t sz = sizeof(T);
+  const int64_t ld = h->ld, K = h->K, M = h->M;
+  Plan local;
+  Plan& pl = cacheable ? h->plan : local;
+  const bool hit = cacheable && pl.fold_begin == f0 && pl.fold_end == f1 && pl.want == want && pl.csr_version == h->csr_version;
+  if (!hit) {
+    plan_tiles(h, want, pl.tiles);
+    plan_units(h, off, f0, f1, (int)pl.tiles.size(), pl);
+    pl.fold_begin = f0; pl.fold_end = f1; pl.want = want; pl.csr_version = h->csr_version;
+  }
+  CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
+  CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
+  CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
+  CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
+  if (h->flags != 0) {
+    for (int64_t c0 = 0; c0 < Pn; c0 += 0x7fffffff) {
+      const int64_t nb = std::min<int64_t>(0x7fffffff, Pn - c0);
+      k_weight_mass<T><<<(unsigned)nb, PW_THREADS, 0, h->stream>>>(
+          h->Z.as<T>(), h->w.as<T>(), ld, h->N, K, M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
+          h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
+      h->launches++;
+    }
+    CU(h, cudaGetLastError());
+    MomentParams<T> mp;
+    mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
+    mp.offsets = d_off; mp.indices = d_idx; mp.fold0 = f0; mp.N = h->N;
+    mp.flags = h->flags; mp.resolution = (T)h->resolution;
+    mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+    mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
+    int32_t rc = launch_moments<T>(h, mp, Pn, pl.max_rows);
+    if (rc) return rc;
+  }
+  if (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) {
+    EpiParams<T> epi;
+    epi.mode = 1; epi.flags = h->flags; epi.want = want;
+    epi.K = K; epi.M = M; epi.ld = ld;
+    epi.Ttot = h->Ttot.as<T>(); epi.stats = h->stats.as<T>(); epi.fs = h->fscal.as<FoldScalars>();
+    epi.out_xx = dxx; epi.xx_pitch = K; epi.xx_stride = K * K;
+    epi.out_xy = dxy; epi.xy_pitch = M; epi.xy_stride = K * M;
+    // the Gram kernel reads fold rows through absolute CSR positions
+    int32_t rc = launch_gram<T>(h, pl, d_idx, epi);
+    if (rc) return rc;
+  }
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t export_small(cvmx_t* h, int64_t Pn, void* out_stats, void* out_scal, int32_t* out_status, int32_t mem) {
+  const size_t sz = sizeof(T);
+  const int64_t C = h->K + h->M;
+  const cudaMemcpyKind kind = mem == CVMX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (out_stats)
+    CU(h, cudaMemcpy2DAsync(out_stats, C * sz, h->stats.p, h->ld * sz, C * sz, Pn * 2, kind, h->stream));
+  if (out_scal || out_status) {
+    T* dscal = nullptr; int32_t* dstat = nullptr;
+    if (mem == CVMX_HOST) {
+      CU(h, h->out_small.reserve(Pn * (2 * sz + sizeof(int32_t))));
+      dscal = h->out_small.as<T>();
+      dstat = reinterpret_cast<int32_t*>(h->out_small.as<char>() + Pn * 2 * sz);
+    } else { dscal = (T*)out_scal; dstat = out_status; }
+    k_pack_scalars<T><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>(), Pn,
+                                                                           out_scal ? dscal : nullptr, out_status ? dstat : nullptr);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    if (mem == CVMX_HOST) {
+      if (out_scal) CU(h, cudaMemcpyAsync(out_scal, dscal, Pn * 2 * sz, cudaMemcpyDeviceToHost, h->stream));
+      if (out_status) CU(h, cudaMemcpyAsync(out_status, dstat, Pn * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t training_impl(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const int64_t* off, int64_t f0, int64_t f1,
+                      uint32_t want, void* oxx, void* oxy, void* ostats, void* oscal, int32_t* ostatus, int32_t mem,
+                      bool cacheable) {
+  const size_t sz = sizeof(T);
+  const int64_t K = h->K, M = h->M;
+  if ((want & CVMX_WANT_XTY) && M == 0) return fail(h, CVMX_ERR_NO_Y, "Response variables `Y` are not provided.");
+  if ((want & CVMX_WANT_XTX) && !oxx) return fail(h, CVMX_ERR_INVALID, "out_XTX is NULL");
+  if ((want & CVMX_WANT_XTY) && !oxy) return fail(h, CVMX_ERR_INVALID, "out_XTY is NULL");
+  if (mem == CVMX_DEVICE) {
+    int32_t rc = run_folds<T>(h, d_off, d_idx, off, f0, f1, want, (T*)oxx, (T*)oxy, cacheable);
+    if (rc) return rc;
+    return export_small<T>(h, f1 - f0, ostats, oscal, ostatus, mem);
+  }
+  // host outputs: bounded device staging, fold sub-batches
+  const size_t per_fold = ((want & CVMX_WANT_XTX) ? (size_t)K * K : 0) * sz + ((want & CVMX_WANT_XTY) ? (size_t)K * M : 0) * sz;
+  const int64_t chunk = per_fold ? std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / per_fold)) : (f1 - f0);
+  for (int64_t c0 = f0; c0 < f1; c0 += chunk) {
+    const int64_t c1 = std::min(f1, c0 + chunk), Pn = c1 - c0;
+    if (want & CVMX_WANT_XTX) CU(h, h->out_xx.reserve((size_t)Pn * K * K * sz));
+    if (want & CVMX_WANT_XTY) CU(h, h->out_xy.reserve((size_t)Pn * K * M * sz));
+    int32_t rc = run_folds<T>(h, d_off, d_idx, off, c0, c1, want, h->out_xx.as<T>(), h->out_xy.as<T>(),
+                              cacheable && chunk >= f1 - f0);
+    if (rc) return rc;
+    const int64_t d = c0 - f0;
+    if (want & CVMX_WANT_XTX)
+      CU(h, cudaMemcpyAsync((char*)oxx + (size_t)d * K * K * sz, h->out_xx.p, (size_t)Pn * K * K * sz, cudaMemcpyDeviceToHost, h->stream));
+    if (want & CVMX_WANT_XTY)
+      CU(h, cudaMemcpyAsync((char*)oxy + (size_t)d * K * M * sz, h->out_xy.p, (size_t)Pn * K * M * sz, cudaMemcpyDeviceToHost, h->stream));
+    rc = export_small<T>(h, Pn, ostats ? (char*)ostats + (size_t)d * 2 * (K + M) * sz : nullptr,
+                         oscal ? (char*)oscal + (size_t)d * 2 * sz : nullptr, ostatus ? ostatus + d : nullptr, mem);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return CVMX_OK;
+}
+
+// offsets: always a host array here; indices: host or device according to `mem`
+int32_t upload_csr(cvmx_t* h, DevBuf& doff, DevBuf& didx, const int64_t* offsets, const int64_t* indices, int64_t P,
+                   int64_t nidx, int32_t mem) {
+  CU(h, doff.reserve((P + 1) * sizeof(int64_t)));
+  CU(h, didx.reserve(std::max<int64_t>(nidx, 1) * sizeof(int64_t)));
+  CU(h, h->errflag.reserve(sizeof(int32_t)));
+  const cudaMemcpyKind kind = mem == CVMX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CU(h, cudaMemcpyAsync(doff.p, offsets, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->errflag.p, 0, sizeof(int32_t), h->stream));
+  if (nidx > 0) {
+    CU(h, cudaMemcpyAsync(didx.p, indices, nidx * sizeof(int64_t), kind, h->stream));
+    k_normalize_indices<<<(unsigned)((nidx + 255) / 256), 256, 0, h->stream>>>(didx.as<int64_t>(), nidx, h->N, h->errflag.as<int32_t>());
+    h->launches++;
+    CU(h, cudaGetLastError());
+  }
+  int32_t bad = 0;
+  CU(h, cudaMemcpyAsync(&bad, h->errflag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (bad) return fail(h, CVMX_ERR_INDEX, "validation index out of bounds for the fitted number of rows");
+  return CVMX_OK;
+}
+
+}  // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t cvmx_version(void) { return CVMX_VERSION; }
+
+const char* cvmx_last_error(const cvmx_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof, double resolution, cvmx_t** out) {
+  if (!out) return fail(nullptr, CVMX_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (dtype != CVMX_F32 && dtype != CVMX_F64) return fail(nullptr, CVMX_ERR_INVALID, "dtype must be CVMX_F32 or CVMX_F64");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CVMX_ERR_CUDA, std::string("no CUDA device: libcvmx has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= ndev) return fail(nullptr, CVMX_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, CVMX_ERR_CUDA, std::string("libcvmx is built for sm_100a (B200) only; found ") + prop.name);
+  cvmx_t* h = new cvmx_handle();
+  h->device = device; h->dtype = dtype; h->flags = flags & 15u; h->ddof = ddof; h->resolution = resolution;
+  h->sm_count = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
+  }
+  h->stream = h->own_stream;
+  *out = h;
+  return CVMX_OK;
+}
+
+int32_t cvmx_destroy(cvmx_t* h) {
+  if (!h) return CVMX_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+                    &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->fscal, &h->pwcols,
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small})
+    b->release();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return CVMX_OK;
+}
+
+int32_t cvmx_set_stream(cvmx_t* h, void* s) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  cudaStreamSynchronize(h->stream);
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return CVMX_OK;
+}
+
+int32_t cvmx_sync(cvmx_t* h) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return CVMX_OK;
+}
+
+int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M, int64_t ldy,
+                 const void* w, int32_t mem, int64_t g0, int64_t g1) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  if (!X || N < 0 || K <= 0 || ldx < K || M < 0 || (M > 0 && (!Y || ldy < M)) || g0 < 0 || g1 > N || g0 > g1)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_fit: bad shape arguments");
+  CU(h, cudaSetDevice(h->device));
+  if (!Y) M = 0;
+  return h->dtype == CVMX_F64 ? fit_impl<double>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1)
+                              : fit_impl<float>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1);
+}
+
+int32_t cvmx_totals_ptr(cvmx_t* h, void** p, int64_t* count, int64_t* ld) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_totals_ptr: fit first");
+  if (p) *p = h->Ttot.p;
+  if (count) *count = h->K * h->ld;
+  if (ld) *ld = h->ld;
+  return CVMX_OK;
+}
+
+int32_t cvmx_commit_totals(cvmx_t* h) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_commit_totals: fit first");
+  return CVMX_OK;  // totals are consumed in place; kept as an explicit step of the sharded-fit protocol
+}
+
+int32_t cvmx_get_totals(cvmx_t* h, void* XTX, void* XTY, void* sum_X, void* sum_Y, void* sum_sq_X, void* sum_sq_Y,
+                        double* sum_w, int64_t* nnz_w) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_get_totals: fit first");
+  CU(h, cudaSetDevice(h->device));
+  const size_t sz = esz(h);
+  const int64_t K = h->K, M = h->M, ld = h->ld;
+  const char* T = h->Ttot.as<char>();
+  if (XTX) CU(h, cudaMemcpy2DAsync(XTX, K * sz, T, ld * sz, K * sz, K, cudaMemcpyDeviceToHost, h->stream));
+  if (XTY && M) CU(h, cudaMemcpy2DAsync(XTY, M * sz, T + K * sz, ld * sz, M * sz, K, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_X) CU(h, cudaMemcpyAsync(sum_X, h->sum_z.p, K * sz, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_Y && M) CU(h, cudaMemcpyAsync(sum_Y, h->sum_z.as<char>() + K * sz, M * sz, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_sq_X) CU(h, cudaMemcpyAsync(sum_sq_X, h->sumsq_z.p, K * sz, cudaMemcpyDeviceToHost, h->stream));
+  if (sum_sq_Y && M) CU(h, cudaMemcpyAsync(sum_sq_Y, h->sumsq_z.as<char>() + K * sz, M * sz, cudaMemcpyDeviceToHost, h->stream));
+  FitScalars fsc;
+  CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (sum_w) *sum_w = fsc.sum_w;
+  if (nnz_w) *nnz_w = fsc.nnz_w;
+  return CVMX_OK;
+}
+
+int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P, int32_t mem) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_set_folds: fit first");
+  if (!offsets || P < 0) return fail(h, CVMX_ERR_INVALID, "cvmx_set_folds: bad arguments");
+  CU(h, cudaSetDevice(h->device));
+  h->h_off.resize(P + 1);
+  if (mem == CVMX_HOST) std::memcpy(h->h_off.data(), offsets, (P + 1) * sizeof(int64_t));
+  else CU(h, cudaMemcpy(h->h_off.data(), offsets, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (h->h_off[0] != 0) return fail(h, CVMX_ERR_INVALID, "offsets[0] must be 0");
+  for (int64_t f = 0; f < P; ++f)
+    if (h->h_off[f + 1] < h->h_off[f]) return fail(h, CVMX_ERR_INVALID, "offsets must be non-decreasing");
+  const int64_t nidx = h->h_off[P];
+  if (nidx > 0 && !indices) return fail(h, CVMX_ERR_INVALID, "indices is NULL");
+  h->P = 0; h->csr_version++;
+  int32_t rc = upload_csr(h, h->d_off, h->d_idx, h->h_off.data(), indices, P, nidx, mem);
+  if (rc) return rc;
+  h->P = P;
+  return CVMX_OK;
+}
+
+int32_t cvmx_training_batch(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, void* oxx, void* oxy, void* ostats, void* oscal,
+                            int32_t* ostatus, int32_t mem) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_training_batch: fit first");
+  if (f0 < 0 || f1 > h->P || f0 > f1) return fail(h, CVMX_ERR_INVALID, "cvmx_training_batch: fold range outside the CSR");
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64
+             ? training_impl<double>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), h->h_off.data(), f0, f1, want, oxx, oxy,
+                                     ostats, oscal, ostatus, mem, true)
+             : training_impl<float>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), h->h_off.data(), f0, f1, want, oxx, oxy,
+                                    ostats, oscal, ostatus, mem, true);
+}
+
+int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val, int64_t n_val, int32_t idx_mem, uint32_t want, void* oxx, void* oxy,
+                              void* ostats, void* oscal, int32_t* ostatus, int32_t out_mem) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_training_indices: fit first");
+  if (n_val < 0 || (n_val > 0 && !val)) return fail(h, CVMX_ERR_INVALID, "cvmx_training_indices: bad arguments");
+  CU(h, cudaSetDevice(h->device));
+  const int64_t off[2] = {0, n_val};
+  int32_t rc = upload_csr(h, h->a_off, h->a_idx, off, val, 1, n_val, idx_mem);
+  if (rc) return rc;
+  return h->dtype == CVMX_F64
+             ? training_impl<double>(h, h->a_off.as<int64_t>(), h->a_idx.as<int64_t>(), off, 0, 1, want, oxx, oxy, ostats, oscal,
+                                     ostatus, out_mem, false)
+             : training_impl<float>(h, h->a_off.as<int64_t>(), h->a_idx.as<int64_t>(), off, 0, 1, want, oxx, oxy, ostats, oscal,
+                                    ostatus, out_mem, false);
+}
+
+int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }
+int64_t cvmx_ld(const cvmx_t* h) { return h ? h->ld : 0; }
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// Weighted Gram kernel on the FP64 tensor cores (DMMA.8x8x4) with the fused fold epilogue.
+//
+//   G[i][j] = sum_{r in rows} rn(w_r * x_ri) * z_rj        i < K, j < K + M, z = [x | y]
+//
+// is the contraction behind XTX = WX.T @ X, XTY = WX.T @ Y (cvmatrix/cvmatrix.py:1215-1217) and
+// behind the per-fold downdate X_val.T @ mat2_val (cvmatrix/cvmatrix.py:1001).  One CTA owns one
+// 128 x 128 output tile of one (fold, row-split) unit; only tiles on or above the diagonal are
+// computed and the XTX part is mirrored on store.  The epilogue applies, per element,
+//   A = T - G ; A -= sw * (mean_i * mean_j) ; A /= (std_i * std_j)       (cvmatrix.py:1001-1009)
+// with each operation individually rounded in the model dtype, exactly as numpy evaluates it.
+#pragma once
+#include "common.cuh"
+
+namespace cvmx {
+
+constexpr int GB = 128;       // tile edge (output rows and columns per CTA)
+constexpr int GBK = 16;       // data rows (reduction index) per pipeline stage
+constexpr int GSTAGES = 4;    // cp.async ring depth
+constexpr int GTHREADS = 256; // 8 warps = 2 (rows) x 4 (cols), warp tile 64 x 32
+constexpr int GACC = 64;      // accumulator doubles per thread
+constexpr int GTILE_ELEMS = GB * GB;
+
+template <typename T> struct GramCfg;
+// PITCH: shared-memory row pitch of a staged data-row segment, chosen so that the MMA fragment
+// loads (lane -> row l%4, column pair 2*(l/4)) hit distinct banks: f64 LDS.128 needs pitch/2 = 2 (mod 8)
+// in 16-byte units -> pitch = 4 (mod 16) doubles; f32 LDS.64 needs pitch/2 = 4 (mod 16) in 8-byte units.
+template <> struct GramCfg<double> { static constexpr int PITCH = 132; static constexpr int CPITCH = 130; typedef double2 vec2; };
+template <> struct GramCfg<float>  { static constexpr int PITCH = 136; static constexpr int CPITCH = 130; typedef float2 vec2; };
+
+struct GramUnit {          // one (fold, row-split): a contiguous range of the CSR index array
+  int64_t row_begin;       // position in `indices` (or absolute row when indices == nullptr)
+  int64_t row_end;
+  int32_t fold;            // fold number relative to the batch
+  int32_t split;           // 0 .. nsplit-1
+  int32_t nsplit;          // 1: fused epilogue in k_gram; >1: partials + k_gram_reduce
+  int32_t part_base;       // index of split 0 of this fold in the partial workspace
+};
+
+template <typename T>
+struct EpiParams {
+  int mode;                // 0: raw Gram (fit totals)   1: fold downdate + centering + scaling
+  uint32_t flags;          // cX | cY<<1 | sX<<2 | sY<<3
+  uint32_t want;           // CVMX_WANT_XTX | CVMX_WANT_XTY
+  int64_t K, M, ld;
+  const T* Ttot;           // K x ld totals [XtWX | XtWY]
+  const T* stats;          // [P][2][ld] mean, std of the fold's training set
+  const FoldScalars* fs;   // [P]
+  T* out_xx; int64_t xx_pitch; int64_t xx_stride;   // fold f, row i, col j -> out_xx[f*stride + i*pitch + j]
+  T* out_xy; int64_t xy_pitch; int64_t xy_stride;
+};
+
+template <typename T>
+struct GramParams {
+  const T* Z; const T* w; int64_t ld;
+  const int64_t* indices;
+  const GramUnit* units;
+  const int2* tiles; int ntiles;
+  double* partials;        // [n_partial_units][ntiles][GACC][GTHREADS]
+  EpiParams<T> epi;
+};
+
+template <typename T>
+constexpr size_t gram_smem_bytes() {
+  size_t pipe = sizeof(T) * ((size_t)2 * GSTAGES * GBK * GramCfg<T>::PITCH + (size_t)GSTAGES * GBK);
+  size_t stage = sizeof(T) * (size_t)GB * GramCfg<T>::CPITCH;
+  return pipe > stage ? pipe : stage;
+}
+
+// Epilogue of one 128 x 128 tile.
+//  pass 1  accumulator fragments -> shared tile sC (raw G, model dtype).  m-tile t covers tile rows
+//          wm*64 + 16*(t/2) + 2*g + (t%2); n-tile u covers tile columns wn*32 + 16*(u/2) + 2*h + (u%2) with h the
+//          B-fragment column; in the accumulator h = 2*q + e, so a lane owns 4 consecutive columns per (t, u/2).
+//  pass 2  in place, one column pair per thread step:  A = T - G ; A -= sw*(m_i*m_j) ; A /= (s_i*s_j)
+//          (each op individually rounded; cvmatrix/cvmatrix.py:1001-1009).  Diagonal tiles skip the lower half.
+//  pass 3  coalesced stores: the tile itself (a diagonal tile takes its lower half from the upper half, so the
+//          result is exactly symmetric) and, for off-diagonal tiles, the mirrored XTX block.
+template <typename T>
+__device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, const EpiParams<T>& e, int fold, int bi,
+                                              int bj) {
+  constexpr int CP = GramCfg<T>::CPITCH;
+  typedef typename GramCfg<T>::vec2 vec2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+  const int64_t K = e.K, C = e.K + e.M, ld = e.ld;
+  const bool diag = bi == bj;
+
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int r = wm * 64 + 16 * (t >> 1) + 2 * g + (t & 1);
+#pragma unroll
+    for (int up = 0; up < 2; ++up) {
+      const int cb = wn * 32 + up * 16 + 4 * q;
+      vec2 lo, hi;
+      lo.x = (T)acc[t][2 * up][0]; lo.y = (T)acc[t][2 * up + 1][0];
+      hi.x = (T)acc[t][2 * up][1]; hi.y = (T)acc[t][2 * up + 1][1];
+      *reinterpret_cast<vec2*>(sC + r * CP + cb) = lo;
+      *reinterpret_cast<vec2*>(sC + r * CP + cb + 2) = hi;
+    }
+  }
+  __syncthreads();
+
+  if (e.mode == 1) {
+    const bool cX = e.flags & 1, cY = e.flags & 2, sX = e.flags & 4, sY = e.flags & 8;
+    const T* mean = e.stats + (size_t)fold * 2 * ld;
+    const T* sdev = mean + ld;
+    const T sw = (T)e.fs[fold].sw;
+#pragma unroll 1
+    for (int idx = tid; idx < GTILE_ELEMS / 2; idx += GTHREADS) {
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      const int64_t i = (int64_t)bi * GB + r, j = (int64_t)bj * GB + c;
+      if (i >= K || j >= C || (diag && c + 1 < r)) continue;
+      vec2 gv = *reinterpret_cast<const vec2*>(sC + r * CP + c);
+      const vec2 tv = *reinterpret_cast<const vec2*>(e.Ttot + i * ld + j);
+      const vec2 mj = *reinterpret_cast<const vec2*>(mean + j);
+      const vec2 sj = *reinterpret_cast<const vec2*>(sdev + j);
+      const T mi = mean[i], si = sdev[i];
+      T a[2] = {Rn<T>::sub(tv.x, gv.x), Rn<T>::sub(tv.y, gv.y)};
+      const T mjj[2] = {mj.x, mj.y}, sjj[2] = {sj.x, sj.y};
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (j + x < K) {
+          if (cX) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi, mjj[x])));
+          if (sX) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si, sjj[x]));
+        } else {
+          if (cX || cY) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi, mjj[x])));
+          if (sX && sY) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si, sjj[x]));
+          else if (sX) a[x] = Rn<T>::div(a[x], si);
+          else if (sY) a[x] = Rn<T>::div(a[x], sjj[x]);
+        }
+      }
+      gv.x = a[0]; gv.y = a[1];
+      *reinterpret_cast<vec2*>(sC + r * CP + c) = gv;
+    }
+    __syncthreads();
+  }
+
+  const bool wxx = e.want & 1, wxy = e.want & 2;
+  T* oxx = e.out_xx + (size_t)fold * e.xx_stride;
+  T* oxy = e.out_xy + (size_t)fold * e.xy_stride;
+  const bool vec_ok = wxx && (e.xx_pitch % 2 == 0) && (e.xx_stride % 2 == 0) &&
+                      (reinterpret_cast<uintptr_t>(e.out_xx) % (2 * sizeof(T)) == 0);
+#pragma unroll 1
+  for (int idx = tid; idx < GTILE_ELEMS / 2; idx += GTHREADS) {
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    const int64_t i = (int64_t)bi * GB + r, j = (int64_t)bj * GB + c;
+    if (i >= K || j >= C) continue;
+    vec2 v;
+    if (diag && c + 1 < r) { v.x = sC[c * CP + r]; v.y = sC[(c + 1) * CP + r]; }
+    else {
+      v = *reinterpret_cast<const vec2*>(sC + r * CP + c);
+      if (diag && c < r) v.x = sC[c * CP + r];
+    }
+    if (j + 1 < K && vec_ok) {
+      *reinterpret_cast<vec2*>(oxx + i * e.xx_pitch + j) = v;
+    } else {
+      const T vv[2] = {v.x, v.y};
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int64_t jj = j + x;
+        if (jj < K) { if (wxx) oxx[i * e.xx_pitch + jj] = vv[x]; }
+        else if (jj < C && wxy) oxy[i * e.xy_pitch + (jj - K)] = vv[x];
+      }
+    }
+  }
+  if (!diag && wxx) {  // mirrored XTX block: out[j][i] = out[i][j]; lanes run along i so the stores coalesce
+#pragma unroll 1
+    for (int idx = tid; idx < GTILE_ELEMS / 2; idx += GTHREADS) {
+      const int c = (idx >> 7) * 2, r = idx & 127;
+      const int64_t i = (int64_t)bi * GB + r, j = (int64_t)bj * GB + c;
+      if (i >= K || j >= K) continue;
+      const vec2 v = *reinterpret_cast<const vec2*>(sC + r * CP + c);
+      oxx[j * e.xx_pitch + i] = v.x;
+      if (j + 1 < K) oxx[(j + 1) * e.xx_pitch + i] = v.y;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PITCH = GramCfg<T>::PITCH;
+  typedef typename GramCfg<T>::vec2 vec2;
+  constexpr int EPC = 16 / sizeof(T);        // elements per 16-byte chunk
+  constexpr int CPR = GB / EPC;              // chunks per staged row segment
+  constexpr int LOADS = GBK * CPR / GTHREADS;
+
+  T* sA = reinterpret_cast<T*>(smem_raw);
+  T* sB = sA + (size_t)GSTAGES * GBK * PITCH;
+  T* sW = sB + (size_t)GSTAGES * GBK * PITCH;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+  const int tile = blockIdx.x % p.ntiles;
+  const GramUnit unit = p.units[blockIdx.x / p.ntiles];
+  const int2 tl = p.tiles[tile];
+  const int bi = tl.x, bj = tl.y;
+  const bool diag = bi == bj;
+  const int64_t ld = p.ld;
+  const int64_t nk = (unit.row_end - unit.row_begin + GBK - 1) / GBK;
+
+  auto load_stage = [&](int64_t kt) {
+    if (kt < nk) {
+      const int slot = (int)(kt % GSTAGES);
+      const int64_t k0 = unit.row_begin + kt * GBK;
+#pragma unroll
+      for (int j = 0; j < LOADS; ++j) {
+        const int c = tid + j * GTHREADS;
+        const int r = c / CPR, ch = c % CPR;
+        const int64_t pos = k0 + r;
+        const bool ok = pos < unit.row_end;
+        const int64_t grow = ok ? (p.indices ? p.indices[pos] : pos) : 0;
+        const T* src = p.Z + grow * ld;
+        const int64_t colA = (int64_t)bi * GB + ch * EPC;
+        const bool okA = ok && colA < ld;
+        cp_async16(sA + ((size_t)slot * GBK + r) * PITCH + ch * EPC, okA ? src + colA : p.Z, okA ? 16 : 0);
+        if (!diag) {
+          const int64_t colB = (int64_t)bj * GB + ch * EPC;
+          const bool okB = ok && colB < ld;
+          cp_async16(sB + ((size_t)slot * GBK + r) * PITCH + ch * EPC, okB ? src + colB : p.Z, okB ? 16 : 0);
+        }
+      }
+      if (tid < GBK) {
+        const int64_t pos = k0 + tid;
+        const bool ok = pos < unit.row_end;
+        const int64_t grow = ok ? (p.indices ? p.indices[pos] : pos) : 0;
+        if (sizeof(T) == 8) cp_async8(sW + slot * GBK + tid, p.w + grow, ok ? 8 : 0);
+        else cp_async4(sW + slot * GBK + tid, p.w + grow, ok ? 4 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) load_stage(s);
+
+  for (int64_t kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    load_stage(kt + GSTAGES - 1);
+    const int slot = (int)(kt % GSTAGES);
+    const T* a_base = sA + (size_t)slot * GBK * PITCH + wm * 64 + 2 * g;
+    const T* b_base = (diag ? sA : sB) + (size_t)slot * GBK * PITCH + wn * 32 + 2 * g;
+    const T* w_base = sW + slot * GBK;
+#pragma unroll
+    for (int kk = 0; kk < GBK / 4; ++kk) {
+      const int k = kk * 4 + q;
+      const T wv = w_base[k];
+      double a[8], b[4];
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        const vec2 v = *reinterpret_cast<const vec2*>(a_base + k * PITCH + tp * 16);
+        a[2 * tp] = (double)Rn<T>::mul(v.x, wv);       // rn(w*x) in the model dtype == WX of the reference
+        a[2 * tp + 1] = (double)Rn<T>::mul(v.y, wv);
+      }
+#pragma unroll
+      for (int up = 0; up < 2; ++up) {
+        const vec2 v = *reinterpret_cast<const vec2*>(b_base + k * PITCH + up * 16);
+        b[2 * up] = (double)v.x;
+        b[2 * up + 1] = (double)v.y;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  if (unit.nsplit == 1) {
+    gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
+  } else {
+    double* dst = p.partials + ((size_t)(unit.part_base + unit.split) * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dst[((t * 4 + u) * 2 + 0) * GTHREADS + tid] = acc[t][u][0];
+        dst[((t * 4 + u) * 2 + 1) * GTHREADS + tid] = acc[t][u][1];
+      }
+  }
+}
+
+// Split folds: sum the row-split partials of one (fold, tile) in split order (deterministic) and run
+// the same epilogue.  grid = (ntiles, folds-with-splits); fold_units[f] = index of the fold's first unit.
+template <typename T>
+__global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T> p, const int32_t* __restrict__ fold_units,
+                                                             const int32_t* __restrict__ fold_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int fold = fold_list[blockIdx.y];
+  const GramUnit unit = p.units[fold_units[fold]];
+  const int2 tl = p.tiles[tile];
+  double acc[8][4][2];
+  const double* src = p.partials + ((size_t)unit.part_base * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
+  const size_t split_stride = (size_t)p.ntiles * GACC * GTHREADS;
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[t][u][0] = src[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
+      acc[t][u][1] = src[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
+    }
+  for (int s = 1; s < unit.nsplit; ++s) {
+    const double* ps = src + s * split_stride;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
+        acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
+      }
+  }
+  gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, tl.x, tl.y);
+}
+
+// CSR index normalisation: numpy wrap-around for negative indices, error flag for out-of-range ones.
+__global__ void k_normalize_indices(int64_t* __restrict__ idx, int64_t n, int64_t N, int32_t* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = idx[i];
+  if (v < 0) v += N;
+  if (v < 0 || v >= N) { *err = 1; v = 0; }
+  idx[i] = v;
+}
+
+template <typename T>
+__global__ void k_fill(T* __restrict__ p, int64_t n, T v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace cvmx

@@ -1,0 +1,369 @@
+// Statistics kernels: numpy-order weight sums and column moments, per-fold means / stds.
+//
+// Parity with the reference hinges on the ORDER of these reductions:
+//   * sum of weights (np.sum of an (n,1) array)        -> numpy pairwise summation
+//   * column sums over rows (np.sum(A, axis=0), C >= 2) -> strictly sequential in row order
+//   * C == 1                                            -> pairwise again
+// and on every elementwise op being individually rounded (Rn<T>, no FMA contraction).
+// Reference: cvmatrix/cvmatrix.py:589-630 (weight mass), :632-752 (fold statistics),
+// :1045-1129 (divisor, std), :1219-1243 (fit moments).
+#pragma once
+#include "common.cuh"
+
+namespace cvmx {
+
+constexpr int PW_THREADS = 256;  // 2^8 sub-trees of the pairwise recursion per block
+constexpr int PW_LEVELS = 8;
+
+// Functor over "element i of the reduced vector" for the three quantities numpy sums pairwise.
+template <typename T>
+struct PwSrc {
+  const T* Z;          // N x ld, [X | Y | pad]
+  const T* w;          // N (all ones when the model is unweighted)
+  const int64_t* idx;  // row list (nullptr: identity)
+  int64_t ld;
+  int64_t col;
+  int kind;  // 0: w   1: rn(w*z)   2: rn(rn(w*z)*z)
+  __device__ __forceinline__ T operator()(int64_t i) const {
+    const int64_t r = idx ? idx[i] : i;
+    const T wr = w[r];
+    if (kind == 0) return wr;
+    const T z = Z[r * ld + col];
+    const T wz = Rn<T>::mul(z, wr);
+    return kind == 1 ? wz : Rn<T>::mul(wz, z);
+  }
+};
+
+template <typename T, typename F>
+__device__ T pw_leaf(const F& f, int64_t off, int64_t n) {
+  if (n < 8) {
+    T r = T(0);
+    for (int64_t i = 0; i < n; ++i) r = Rn<T>::add(r, f(off + i));
+    return r;
+  }
+  T r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = f(off + j);
+  const int64_t stop = n - (n % 8);
+  for (int64_t i = 8; i < stop; i += 8) {
+    T v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = f(off + i + j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = Rn<T>::add(r[j], v[j]);
+  }
+  T res = Rn<T>::add(Rn<T>::add(Rn<T>::add(r[0], r[1]), Rn<T>::add(r[2], r[3])),
+                     Rn<T>::add(Rn<T>::add(r[4], r[5]), Rn<T>::add(r[6], r[7])));
+  for (int64_t i = stop; i < n; ++i) res = Rn<T>::add(res, f(off + i));
+  return res;
+}
+
+// numpy's recursion (split at n/2 rounded down to a multiple of 8 while n > 128), walked with an
+// explicit stack so no device call stack is needed.
+template <typename T, typename F>
+__device__ T pw_serial(const F& f, int64_t off0, int64_t n0) {
+  constexpr int MAXD = 48;
+  int64_t offs[MAXD], lens[MAXD];
+  T accs[MAXD];
+  signed char st[MAXD];
+  int sp = 0;
+  offs[0] = off0; lens[0] = n0; st[0] = 0; sp = 1;
+  T ret = T(0);
+  while (sp > 0) {
+    const int top = sp - 1;
+    const int64_t n = lens[top];
+    if (st[top] == 0) {
+      if (n <= 128) { ret = pw_leaf<T>(f, offs[top], n); --sp; continue; }
+      int64_t n2 = n / 2; n2 -= n2 % 8;
+      st[top] = 1;
+      offs[sp] = offs[top]; lens[sp] = n2; st[sp] = 0; ++sp;
+    } else if (st[top] == 1) {
+      accs[top] = ret;
+      int64_t n2 = n / 2; n2 -= n2 % 8;
+      st[top] = 2;
+      offs[sp] = offs[top] + n2; lens[sp] = n - n2; st[sp] = 0; ++sp;
+    } else {
+      ret = Rn<T>::add(accs[top], ret);
+      --sp;
+    }
+  }
+  return ret;
+}
+
+// Whole-block evaluation of the same tree: thread j walks PW_LEVELS levels down along the bits of j,
+// sums its sub-tree serially, then the sub-tree values are combined bottom-up in exactly the order the
+// recursion would (left + right).  Result is valid in thread 0 (and in s_val[0]).
+template <typename T, typename F>
+__device__ T block_pairwise(const F& f, int64_t n, T* s_val, unsigned char* s_valid) {
+  const int tid = threadIdx.x;
+  int64_t off = 0, len = n;
+  bool owner = true;
+  for (int level = 0; level < PW_LEVELS; ++level) {
+    if (len <= 128) {
+      owner = (tid & ((1 << (PW_LEVELS - level)) - 1)) == 0;
+      break;
+    }
+    int64_t n2 = len / 2; n2 -= n2 % 8;
+    if ((tid >> (PW_LEVELS - 1 - level)) & 1) { off += n2; len -= n2; } else { len = n2; }
+  }
+  __syncthreads();  // s_val may be reused between calls
+  s_val[tid] = owner ? pw_serial<T>(f, off, len) : T(0);
+  s_valid[tid] = owner ? 1 : 0;
+  __syncthreads();
+  for (int s = 1; s < PW_THREADS; s <<= 1) {
+    if ((tid & (2 * s - 1)) == 0 && s_valid[tid + s]) s_val[tid] = Rn<T>::add(s_val[tid], s_val[tid + s]);
+    __syncthreads();
+  }
+  return Rn<T>::add(T(0), s_val[0]);  // numpy seeds add-reductions with +0
+}
+
+struct FitScalars {  // device-resident fit totals
+  double sum_w;      // model-dtype value widened to double
+  int64_t nnz_w;
+  int32_t neg_weight;  // any(w < 0)
+  int32_t pad;
+};
+
+// One block per fold (or one block for the whole data set when fit_mode): pairwise weight sum,
+// non-zero count, the derived training scalars, and - for K == 1 / M == 1 - the pairwise column sums.
+//   pw_cols[f][4] = { sum wx, sum wx*x, sum wy, sum wy*y } over the fold rows (only the C == 1 ones are used)
+template <typename T>
+__global__ void __launch_bounds__(PW_THREADS)
+k_weight_mass(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t N, int64_t K, int64_t M,
+              int weighted, const int64_t* __restrict__ offsets, const int64_t* __restrict__ indices,
+              int64_t fold0, int fit_mode, int64_t ddof, FitScalars* __restrict__ fit, FoldScalars* __restrict__ fs,
+              T* __restrict__ pw_cols) {
+  __shared__ T s_val[PW_THREADS];
+  __shared__ unsigned char s_valid[PW_THREADS];
+  __shared__ long long s_cnt[2];
+  const int tid = threadIdx.x;
+  const int64_t f = blockIdx.x;
+  const int64_t beg = fit_mode ? 0 : offsets[fold0 + f];
+  const int64_t n = fit_mode ? N : offsets[fold0 + f + 1] - beg;
+  const int64_t* idx = fit_mode ? nullptr : indices + beg;
+
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  T swv = T(0);
+  if (weighted) {
+    long long nz = 0, neg = 0;
+    for (int64_t i = tid; i < n; i += PW_THREADS) {
+      const T v = w[idx ? idx[i] : i];
+      nz += (v != T(0));
+      neg += (v < T(0));
+    }
+    if (nz) atomicAdd((unsigned long long*)&s_cnt[0], (unsigned long long)nz);
+    if (neg) atomicAdd((unsigned long long*)&s_cnt[1], (unsigned long long)neg);
+    PwSrc<T> src{Z, w, idx, ld, 0, 0};
+    swv = block_pairwise<T>(src, n, s_val, s_valid);
+  }
+  T cols[4] = {T(0), T(0), T(0), T(0)};
+  if (K == 1) {
+    PwSrc<T> a{Z, w, idx, ld, 0, 1}, b{Z, w, idx, ld, 0, 2};
+    cols[0] = block_pairwise<T>(a, n, s_val, s_valid);
+    cols[1] = block_pairwise<T>(b, n, s_val, s_valid);
+  }
+  if (M == 1) {
+    PwSrc<T> a{Z, w, idx, ld, K, 1}, b{Z, w, idx, ld, K, 2};
+    cols[2] = block_pairwise<T>(a, n, s_val, s_valid);
+    cols[3] = block_pairwise<T>(b, n, s_val, s_valid);
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  if (pw_cols)
+    for (int j = 0; j < 4; ++j) pw_cols[f * 4 + j] = cols[j];
+  if (fit_mode) {
+    fit->sum_w = weighted ? (double)swv : (double)N;
+    fit->nnz_w = weighted ? (int64_t)s_cnt[0] : N;
+    fit->neg_weight = s_cnt[1] != 0;
+    return;
+  }
+  T sw, nz;
+  int32_t status = 0;
+  if (weighted) {
+    sw = Rn<T>::sub((T)fit->sum_w, swv);
+    nz = (T)(fit->nnz_w - (int64_t)s_cnt[0]);
+    if (nz == T(0)) status |= 1;
+  } else {
+    sw = nz = (T)(N - n);
+  }
+  if (nz <= (T)ddof) status |= 2;
+  const T dv = Rn<T>::div(Rn<T>::mul(Rn<T>::sub(nz, (T)ddof), sw), nz);
+  FoldScalars o;
+  o.sw = (double)sw; o.nz = (double)nz; o.div = (double)dv; o.status = status; o.pad = 0;
+  fs[f] = o;
+}
+
+// ---- per-column finalisation shared by both moment kernels ----------------------------------------
+template <typename T>
+struct MomentParams {
+  const T* Z; const T* w; int64_t ld; int64_t K; int64_t M;
+  const int64_t* offsets; const int64_t* indices; int64_t fold0;  // fit mode: offsets == nullptr, rows [0, N)
+  int64_t N;
+  uint32_t flags;
+  T resolution;
+  T* sum_z; T* sumsq_z;        // [ld] totals (written in fit mode, read otherwise)
+  const FoldScalars* fs;       // per fold (fold mode)
+  const T* pw_cols;            // per fold pairwise column sums for K == 1 / M == 1
+  T* stats;                    // [P][2][ld]: mean, std
+};
+
+template <typename T>
+__device__ __forceinline__ void finalize_column(const MomentParams<T>& p, int64_t f, int64_t c, T s, T q) {
+  const int64_t C = p.K + p.M;
+  if (c >= C) return;
+  const bool isX = c < p.K;
+  if (p.pw_cols) {
+    if (isX && p.K == 1) { s = p.pw_cols[f * 4 + 0]; q = p.pw_cols[f * 4 + 1]; }
+    if (!isX && p.M == 1) { s = p.pw_cols[f * 4 + 2]; q = p.pw_cols[f * 4 + 3]; }
+  }
+  if (!p.offsets) {  // fit mode
+    p.sum_z[c] = s;
+    p.sumsq_z[c] = q;
+    return;
+  }
+  const bool cX = p.flags & 1, cY = p.flags & 2, sX = p.flags & 4, sY = p.flags & 8;
+  const bool need_mean = isX ? (cX || cY || sX) : (cX || cY || sY);
+  const bool need_std = isX ? sX : sY;
+  T mean = T(0), sd = T(0);
+  if (need_mean) {
+    const T sw = (T)p.fs[f].sw;
+    const T s_train = Rn<T>::sub(p.sum_z[c], s);
+    mean = Rn<T>::div(s_train, sw);
+    if (need_std) {
+      const T dv = (T)p.fs[f].div;
+      const T q_train = Rn<T>::sub(p.sumsq_z[c], q);
+      const T t1 = Rn<T>::mul(Rn<T>::mul(T(-2), mean), s_train);
+      const T t2 = Rn<T>::mul(sw, Rn<T>::mul(mean, mean));
+      T var = Rn<T>::div(Rn<T>::add(Rn<T>::add(t1, t2), q_train), dv);
+      if (!(var >= T(0)) && var == var) var = T(0);  // np.maximum(var, 0) keeps NaN
+      sd = Rn<T>::sqrt(var);
+      if (sd <= p.resolution) sd = T(1);
+    }
+  }
+  T* o = p.stats + (size_t)f * 2 * p.ld;
+  o[c] = mean;
+  o[p.ld + c] = sd;
+}
+
+// ---- small folds: one thread per (fold, column), rows read straight from global ---------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
+  const int64_t f = blockIdx.y;
+  const int64_t c = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (c >= p.ld) return;
+  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
+  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
+  const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
+  T s = T(0), q = T(0);
+  int64_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    int64_t r[4]; T z[4], wv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = idx ? idx[i + j] : i + j;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { z[j] = p.Z[r[j] * p.ld + c]; wv[j] = p.w[r[j]]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const T wz = Rn<T>::mul(z[j], wv[j]);
+      s = Rn<T>::add(s, wz);
+      q = Rn<T>::add(q, Rn<T>::mul(wz, z[j]));
+    }
+  }
+  for (; i < n; ++i) {
+    const int64_t r = idx ? idx[i] : i;
+    const T z = p.Z[r * p.ld + c];
+    const T wz = Rn<T>::mul(z, p.w[r]);
+    s = Rn<T>::add(s, wz);
+    q = Rn<T>::add(q, Rn<T>::mul(wz, z));
+  }
+  finalize_column<T>(p, f, c, s, q);
+}
+
+// ---- long folds: cp.async ring feeds one consumer warp that owns 32 sequential column chains ------
+// The chain (one dependent DADD per row, ~8 cycles on B200) is the critical path; all four warps keep
+// MOM_STAGES x MOM_ROWS gathered row segments in flight so the consumer never waits on HBM.
+constexpr int MOM_COLS = 32;
+constexpr int MOM_ROWS = 32;
+constexpr int MOM_STAGES = 8;
+constexpr int MOM_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sz = reinterpret_cast<T*>(smem_raw);                       // [STAGES][ROWS][COLS]
+  T* swt = sz + (size_t)MOM_STAGES * MOM_ROWS * MOM_COLS;        // [STAGES][ROWS]
+  const int tid = threadIdx.x;
+  const int64_t f = blockIdx.y;
+  const int64_t c0 = (int64_t)blockIdx.x * MOM_COLS;
+  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
+  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
+  const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
+  constexpr int CHUNK = 16 / sizeof(T);               // elements per 16-byte cp.async
+  constexpr int CPR = MOM_COLS / CHUNK;               // chunks per row segment
+  constexpr int PER_THREAD = MOM_ROWS * CPR / MOM_THREADS;
+  const int64_t nst = (n + MOM_ROWS - 1) / MOM_ROWS;
+
+  auto issue = [&](int64_t st) {
+    if (st < nst) {
+      const int slot = (int)(st % MOM_STAGES);
+#pragma unroll
+      for (int j = 0; j < PER_THREAD; ++j) {
+        const int cidx = tid + j * MOM_THREADS;
+        const int r = cidx / CPR, ch = cidx % CPR;
+        const int64_t row = st * MOM_ROWS + r;
+        const bool ok = row < n;
+        const int64_t g = ok ? (idx ? idx[row] : row) : 0;
+        cp_async16(sz + ((size_t)slot * MOM_ROWS + r) * MOM_COLS + ch * CHUNK, p.Z + g * p.ld + c0 + ch * CHUNK,
+                   ok ? 16 : 0);
+      }
+      if (tid < MOM_ROWS) {
+        const int64_t row = st * MOM_ROWS + tid;
+        const bool ok = row < n;
+        const int64_t g = ok ? (idx ? idx[row] : row) : 0;
+        if (sizeof(T) == 8) cp_async8(swt + slot * MOM_ROWS + tid, p.w + g, ok ? 8 : 0);
+        else cp_async4(swt + slot * MOM_ROWS + tid, p.w + g, ok ? 4 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int s = 0; s < MOM_STAGES - 1; ++s) issue(s);
+  T s_acc = T(0), q_acc = T(0);
+  for (int64_t st = 0; st < nst; ++st) {
+    cp_async_wait<MOM_STAGES - 2>();
+    __syncthreads();                 // stage st landed for every thread; slot (st-1) is free again
+    issue(st + MOM_STAGES - 1);
+    if (tid < 32) {
+      const int slot = (int)(st % MOM_STAGES);
+      const T* zr = sz + (size_t)slot * MOM_ROWS * MOM_COLS + tid;
+      const T* wr = swt + slot * MOM_ROWS;
+      const int rows = (int)min((int64_t)MOM_ROWS, n - st * MOM_ROWS);
+      if (rows == MOM_ROWS) {
+#pragma unroll 8
+        for (int r = 0; r < MOM_ROWS; ++r) {
+          const T z = zr[r * MOM_COLS];
+          const T wz = Rn<T>::mul(z, wr[r]);
+          s_acc = Rn<T>::add(s_acc, wz);
+          q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
+        }
+      } else {
+        for (int r = 0; r < rows; ++r) {
+          const T z = zr[r * MOM_COLS];
+          const T wz = Rn<T>::mul(z, wr[r]);
+          s_acc = Rn<T>::add(s_acc, wz);
+          q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (tid < 32) finalize_column<T>(p, f, c0 + tid, s_acc, q_acc);
+}
+
+template <typename T>
+constexpr size_t moments_pipe_smem() {
+  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MOM_COLS + (size_t)MOM_STAGES * MOM_ROWS);
+}
+
+}  // namespace cvmx

@@ -1,0 +1,392 @@
+"""
+CVMatrix on B200: drop-in for ``cvmatrix.CVMatrix`` (reference cvmatrix/cvmatrix.py:99-1243,
+Algorithms 2-7 of Engstrøm & Jensen 2025) whose arithmetic runs in hand-written sm_100a
+kernels behind the C ABI of libcvmx.so (include/cvmx.h).  There is no CPU fallback: the
+class raises at construction when the CUDA library or a B200 is missing.
+
+Same constructor options (center_X, center_Y, scale_X, scale_Y, ddof, dtype, copy), same
+methods (fit, training_XTX, training_XTY, training_XTX_XTY, training_statistics), same return
+structure (fresh numpy arrays of the requested dtype; statistics as (1, K) / (1, M) rows or
+None), same ValueError messages.  Beyond the reference: ``set_folds`` / ``training_batch``
+evaluate many folds in one launch with device-resident outputs (the shape of the reference's
+``jax.vmap`` use, benchmarks/benchmark.py:136-152).
+
+Host code here only marshals arrays, decides which statistics a method returns
+(cvmatrix/cvmatrix.py:563-574, 806-833) and turns per-fold status bits into the reference's
+exceptions (cvmatrix/cvmatrix.py:625-629, 1074-1078).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+from numpy import typing as npt
+
+from . import _lib
+from .partitioner import Partitioner
+
+Array = np.ndarray
+Stats = Tuple[Optional[Array], Optional[Array], Optional[Array], Optional[Array]]
+
+_ERR_NO_NONZERO = "The number of non-zero weights in the training set must be greater than zero."
+_ERR_DDOF = "The number of non-zero weights in the training set must be greater than `ddof`."
+_ERR_NOTHING = "At least one of `return_XTX` and `return_XTY` must be True."
+_ERR_NO_Y = "Response variables `Y` are not provided."
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class CVMatrix:
+    r"""
+    Parameters
+    ----------
+    center_X, center_Y, scale_X, scale_Y : bool, default True
+        Training-set centering / scaling of X and Y inside :math:`X^T W X` and :math:`X^T W Y`
+        (means and standard deviations are those of each fold's training set).
+    ddof : int, default 1
+        Delta degrees of freedom of the weighted standard deviation.
+    dtype : np.float64 (default) or np.float32
+        Model dtype.  Other floating types of the reference's numpy backend (float16, longdouble)
+        have no B200 path and are rejected.
+    copy : bool, default True
+        Same meaning as in the reference for the host-side ``X`` / ``Y`` / ``weights`` attributes;
+        the device always holds its own copy.
+    backend : str, default "numpy"
+        Accepted for signature compatibility.  "numpy" selects the numpy-backend *semantics*, which is
+        the only thing this engine implements; "cuda" is an alias.  "jax" is rejected (no multi-backend
+        dispatch here).
+    device : int, optional
+        CUDA device ordinal (default: the current torch device if torch is imported, else 0).
+    """
+
+    def __init__(
+        self,
+        center_X: bool = True,
+        center_Y: bool = True,
+        scale_X: bool = True,
+        scale_Y: bool = True,
+        ddof: int = 1,
+        dtype: npt.DTypeLike = np.float64,
+        copy: bool = True,
+        backend: str = "numpy",
+        device: Optional[int] = None,
+    ) -> None:
+        if backend not in ("numpy", "cuda"):
+            raise ValueError(f"Invalid backend: {backend!r}. This engine implements the numpy-backend semantics on B200 only.")
+        self.center_X = center_X
+        self.center_Y = center_Y
+        self.scale_X = scale_X
+        self.scale_Y = scale_Y
+        self.ddof = ddof
+        self.dtype = dtype.type if isinstance(dtype, np.dtype) else dtype
+        if np.dtype(self.dtype) not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError(f"dtype {np.dtype(self.dtype).name} has no B200 path; use float64 or float32")
+        self.copy = copy
+        self.backend = backend
+        self.resolution = np.finfo(dtype).resolution * 10
+        self.X = self.Y = self.weights = None
+        self.N = self.K = self.M = None
+        self.XTX = self.XTY = None
+        self.sum_X = self.sum_Y = self.sum_sq_X = self.sum_sq_Y = None
+        self.sum_w = self.num_nonzero_w = None
+
+        self._lib = _lib.load()
+        if device is None:
+            device = 0
+            try:
+                import sys
+
+                if "torch" in sys.modules:
+                    import torch
+
+                    if torch.cuda.is_available():
+                        device = torch.cuda.current_device()
+            except Exception:  # pragma: no cover
+                device = 0
+        self.device = int(device)
+        self._flags = int(bool(center_X)) | int(bool(center_Y)) << 1 | int(bool(scale_X)) << 2 | int(bool(scale_Y)) << 3
+        self._h = C.c_void_p()
+        rc = self._lib.cvmx_create(
+            self.device, _lib.F64 if np.dtype(self.dtype) == np.float64 else _lib.F32, self._flags, int(ddof),
+            float(self.resolution), C.byref(self._h),
+        )
+        _lib.check(rc, None)
+        self._partitioner: Optional[Partitioner] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.cvmx_destroy(h)
+            except Exception:  # pragma: no cover - interpreter shutdown
+                pass
+            self._h = C.c_void_p()
+
+    # ---- fit ---------------------------------------------------------------------------------------
+    def _init_mat(self, mat) -> Array:
+        # cvmatrix/cvmatrix.py:1131-1151
+        mat = np.asarray(mat, dtype=self.dtype)
+        if self.copy and mat.dtype == self.dtype:
+            mat = mat.copy()
+        if mat.ndim == 1:
+            mat = mat.reshape(-1, 1)
+        return mat
+
+    @staticmethod
+    def _rows(a: Array):
+        """(array the library can read, leading dimension in elements): rows must be contiguous."""
+        item = a.dtype.itemsize
+        if (a.shape[0] > 1 and a.shape[1] > 0 and a.strides[1] == item and a.strides[0] % item == 0
+                and a.strides[0] >= a.shape[1] * item):
+            return a, a.strides[0] // item
+        a = np.ascontiguousarray(a)
+        return a, max(a.shape[1], 1)
+
+    def fit(self, X: npt.ArrayLike, Y: Optional[npt.ArrayLike] = None, weights: Optional[npt.ArrayLike] = None,
+            _gram_rows: Optional[Tuple[int, int]] = None) -> None:
+        """cvmatrix/cvmatrix.py:207-328.  Uploads X, Y, weights and computes the dataset-wide totals on the GPU."""
+        self.X = self._init_mat(X)
+        self.N, self.K = self.X.shape
+        if Y is not None:
+            self.Y = self._init_mat(Y)
+            self.M = self.Y.shape[1]
+        else:
+            self.Y = None
+            self.M = None
+        self.weights = self._init_mat(weights) if weights is not None else None
+        if self.Y is not None and self.Y.shape[0] != self.N:
+            raise ValueError("X and Y must have the same number of rows")
+        if self.weights is not None and self.weights.shape[0] != self.N:
+            raise ValueError("weights must have one entry per row of X")
+        self._partitioner = None
+
+        Xd, ldx = self._rows(self.X)
+        Yd, ldy = self._rows(self.Y) if self.Y is not None else (None, 0)
+        wd = np.ascontiguousarray(self.weights.reshape(-1)) if self.weights is not None else None
+        g0, g1 = (0, self.N) if _gram_rows is None else _gram_rows
+        rc = self._lib.cvmx_fit(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST, g0, g1)
+        _lib.check(rc, self._h)
+        self._pull_totals()
+
+    def _pull_totals(self) -> None:
+        dt, K, M = self.dtype, self.K, self.M or 0
+        XTX = np.empty((K, K), dt)
+        XTY = np.empty((K, M), dt) if M else None
+        sX, qX = np.empty((1, K), dt), np.empty((1, K), dt)
+        sY, qY = (np.empty((1, M), dt), np.empty((1, M), dt)) if M else (None, None)
+        sum_w, nnz = C.c_double(), C.c_int64()
+        rc = self._lib.cvmx_get_totals(self._h, _ptr(XTX), _ptr(XTY), _ptr(sX), _ptr(sY), _ptr(qX), _ptr(qY),
+                                       C.byref(sum_w), C.byref(nnz))
+        _lib.check(rc, self._h)
+        cX, cY, sXf, sYf = self.center_X, self.center_Y, self.scale_X, self.scale_Y
+        self.XTX, self.XTY = XTX, XTY
+        # gating of the public attributes: cvmatrix/cvmatrix.py:1223-1243
+        if cX or cY or sXf or sYf:
+            if self.weights is not None:
+                self.sum_w, self.num_nonzero_w = self.dtype(sum_w.value), int(nnz.value)
+            else:
+                self.sum_w, self.num_nonzero_w = self.N, self.N
+        else:
+            self.sum_w = self.num_nonzero_w = None
+        self.sum_X = sX if (cX or cY or sXf) else None
+        self.sum_Y = sY if (M and (cX or cY or sYf)) else None
+        self.sum_sq_X = qX if sXf else None
+        self.sum_sq_Y = qY if (M and sYf) else None
+
+    # Derived N x K host arrays of the reference (cvmatrix/cvmatrix.py:1193-1207, 1235, 1240).  The device
+    # never materialises them (products are formed in registers); they are computed on access.
+    @property
+    def WX(self):
+        if self.X is None:
+            return None
+        return self.X if self.weights is None else self.X * self.weights
+
+    @property
+    def WY(self):
+        if self.Y is None:
+            return None
+        if self.weights is None:
+            return self.Y
+        return self.Y * self.weights if (self.center_X or self.center_Y or self.scale_Y) else None
+
+    @property
+    def sq_X(self):
+        return self.WX * self.X if (self.X is not None and self.scale_X) else None
+
+    @property
+    def sq_Y(self):
+        return self.WY * self.Y if (self.Y is not None and self.scale_Y) else None
+
+    # ---- per-call API (reference signatures) ---------------------------------------------------------
+    def training_XTX(self, validation_indices: npt.NDArray[np.int_]) -> Tuple[Array, Stats]:
+        """cvmatrix/cvmatrix.py:330-383"""
+        return self._training_matrices(True, False, validation_indices)
+
+    def training_XTY(self, validation_indices: npt.NDArray[np.int_]) -> Tuple[Array, Stats]:
+        """cvmatrix/cvmatrix.py:385-449"""
+        return self._training_matrices(False, True, validation_indices)
+
+    def training_XTX_XTY(self, validation_indices: npt.NDArray[np.int_]) -> Tuple[Tuple[Array, Array], Stats]:
+        """cvmatrix/cvmatrix.py:451-517"""
+        return self._training_matrices(True, True, validation_indices)
+
+    def training_statistics(self, validation_indices: npt.NDArray[np.int_]) -> Stats:
+        """cvmatrix/cvmatrix.py:519-574"""
+        self._require_fit()
+        has_Y = self.Y is not None
+        need = (self.center_X or self.scale_X, self.scale_X, (self.center_Y or self.scale_Y) and has_Y, self.scale_Y and has_Y)
+        _, _, stats = self._run_indices(validation_indices, _lib.WANT_STATS, need)
+        return stats
+
+    def _training_matrices(self, return_XTX: bool, return_XTY: bool, val_indices):
+        """cvmatrix/cvmatrix.py:754-896"""
+        if not return_XTX and not return_XTY:
+            raise ValueError(_ERR_NOTHING)
+        self._require_fit()
+        if return_XTY and self.Y is None:
+            raise ValueError(_ERR_NO_Y)
+        cX, cY, sX, sY = self.center_X, self.center_Y, self.scale_X, self.scale_Y
+        need = (cX or (return_XTY and cY), sX, return_XTY and (cX or cY), return_XTY and sY)
+        want = (_lib.WANT_XTX if return_XTX else 0) | (_lib.WANT_XTY if return_XTY else 0) | _lib.WANT_STATS
+        XTX, XTY, stats = self._run_indices(val_indices, want, need)
+        if return_XTX and return_XTY:
+            return (XTX, XTY), stats
+        return (XTX if return_XTX else XTY), stats
+
+    def _require_fit(self):
+        if self.X is None:
+            raise ValueError("fit must be called before the training matrices can be computed")
+
+    @staticmethod
+    def _as_index_array(val) -> np.ndarray:
+        val = np.asarray(val)
+        if val.dtype.kind not in "iu":
+            raise IndexError("arrays used as indices must be of integer type")
+        if val.ndim != 1:
+            val = val.reshape(-1)
+        return np.ascontiguousarray(val, dtype=np.int64)
+
+    def _raise_for_status(self, status: int, need) -> None:
+        any_stat = any(need)
+        if any_stat and self.weights is not None and (status & _lib.FOLD_NO_NONZERO_W):
+            raise ValueError(_ERR_NO_NONZERO)
+        if (need[1] or need[3]) and (status & _lib.FOLD_NNZ_LE_DDOF):
+            raise ValueError(_ERR_DDOF)
+
+    def _split_stats(self, row_pair: np.ndarray, need) -> Stats:
+        K, M = self.K, self.M or 0
+        mean, std = row_pair[0], row_pair[1]
+        return (
+            mean[:K].reshape(1, K).copy() if need[0] else None,
+            std[:K].reshape(1, K).copy() if need[1] else None,
+            mean[K:K + M].reshape(1, M).copy() if need[2] else None,
+            std[K:K + M].reshape(1, M).copy() if need[3] else None,
+        )
+
+    def _run_indices(self, val_indices, want: int, need):
+        val = self._as_index_array(val_indices)
+        dt, K, M = self.dtype, self.K, self.M or 0
+        XTX = np.empty((K, K), dt) if want & _lib.WANT_XTX else None
+        XTY = np.empty((K, M), dt) if want & _lib.WANT_XTY else None
+        stats = np.empty((2, K + M), dt)
+        status = np.zeros(1, np.int32)
+        rc = self._lib.cvmx_training_indices(self._h, _ptr(val), val.size, _lib.HOST, want & 3, _ptr(XTX), _ptr(XTY), _ptr(stats),
+                                             None, _ptr(status), _lib.HOST)
+        _lib.check(rc, self._h)
+        self._raise_for_status(int(status[0]), need)
+        return XTX, XTY, self._split_stats(stats, need)
+
+    # ---- batched API -----------------------------------------------------------------------------------
+    def set_folds(self, folds: Union[Partitioner, Sequence[npt.NDArray[np.int_]]]) -> None:
+        """Uploads all validation index sets as one device-resident CSR (a ``Partitioner`` or a sequence
+        of index arrays)."""
+        self._require_fit()
+        if isinstance(folds, Partitioner):
+            offsets, indices = folds.csr()
+        else:
+            sets = [self._as_index_array(v) for v in folds]
+            offsets = np.zeros(len(sets) + 1, np.int64)
+            if sets:
+                np.cumsum([s.size for s in sets], out=offsets[1:])
+            indices = np.concatenate(sets) if sets else np.zeros(0, np.int64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        rc = self._lib.cvmx_set_folds(self._h, _ptr(offsets), _ptr(indices), offsets.size - 1, _lib.HOST)
+        _lib.check(rc, self._h)
+        self._n_folds = offsets.size - 1
+
+    def training_batch(self, fold_begin: int = 0, fold_end: Optional[int] = None, return_XTX: bool = True,
+                       return_XTY: bool = True, out: str = "numpy", check: bool = True):
+        """
+        All folds ``[fold_begin, fold_end)`` of the CSR in one batched launch.
+
+        Returns a dict with ``XTX`` (P, K, K), ``XTY`` (P, K, M), ``X_mean``/``X_std`` (P, 1, K),
+        ``Y_mean``/``Y_std`` (P, 1, M) (entries the flags do not define are None, exactly as the per-call
+        methods decide), ``sum_w_train`` / ``nnz_train`` (P,) and ``status`` (P,) int32.
+        ``out="numpy"`` copies results to host arrays; ``out="torch"`` leaves them on the device as torch
+        tensors (no host copy; the consumer's next step runs on the GPU).  With ``check`` the degenerate
+        fold errors of the reference are raised for the first offending fold.
+        """
+        self._require_fit()
+        if fold_end is None:
+            fold_end = self._n_folds
+        if not return_XTX and not return_XTY:
+            raise ValueError(_ERR_NOTHING)
+        if return_XTY and self.Y is None:
+            raise ValueError(_ERR_NO_Y)
+        P = fold_end - fold_begin
+        dt, K, M = self.dtype, self.K, self.M or 0
+        want = (_lib.WANT_XTX if return_XTX else 0) | (_lib.WANT_XTY if return_XTY else 0)
+        cX, cY, sX, sY = self.center_X, self.center_Y, self.scale_X, self.scale_Y
+        need = (cX or (return_XTY and cY), sX, return_XTY and (cX or cY), return_XTY and sY)
+        if out == "torch":
+            import torch
+
+            tdt = torch.float64 if np.dtype(dt) == np.float64 else torch.float32
+            dev = torch.device("cuda", self.device)
+            XTX = torch.empty((P, K, K), dtype=tdt, device=dev) if return_XTX else None
+            XTY = torch.empty((P, K, M), dtype=tdt, device=dev) if return_XTY else None
+            stats = torch.empty((P, 2, K + M), dtype=tdt, device=dev)
+            scal = torch.empty((P, 2), dtype=tdt, device=dev)
+            status = torch.empty((P,), dtype=torch.int32, device=dev)
+            p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+            mem = _lib.DEVICE
+            # run stream-ordered with torch so the freshly allocated outputs are safe to write
+            _lib.check(self._lib.cvmx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self._h)
+        elif out == "numpy":
+            XTX = np.empty((P, K, K), dt) if return_XTX else None
+            XTY = np.empty((P, K, M), dt) if return_XTY else None
+            stats = np.empty((P, 2, K + M), dt)
+            scal = np.empty((P, 2), dt)
+            status = np.zeros((P,), np.int32)
+            p = _ptr
+            mem = _lib.HOST
+        else:
+            raise ValueError("out must be 'numpy' or 'torch'")
+        rc = self._lib.cvmx_training_batch(self._h, fold_begin, fold_end, want, p(XTX), p(XTY), p(stats), p(scal), p(status), mem)
+        _lib.check(rc, self._h)
+        if out == "torch":
+            _lib.check(self._lib.cvmx_set_stream(self._h, None), self._h)  # syncs, back to the private stream
+        if check:
+            st = status.cpu().numpy() if out == "torch" else status
+            for s in np.unique(st):
+                if s:
+                    self._raise_for_status(int(s), need)
+        mean, std = stats[:, 0:1, :], stats[:, 1:2, :]
+        return dict(
+            XTX=XTX, XTY=XTY,
+            X_mean=mean[:, :, :K] if need[0] else None, X_std=std[:, :, :K] if need[1] else None,
+            Y_mean=mean[:, :, K:] if need[2] else None, Y_std=std[:, :, K:] if need[3] else None,
+            sum_w_train=scal[:, 0], nnz_train=scal[:, 1], status=status,
+        )
+
+    def sync(self) -> None:
+        _lib.check(self._lib.cvmx_sync(self._h), self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cvmx_launch_count(self._h))

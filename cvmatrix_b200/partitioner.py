@@ -1,0 +1,123 @@
+"""
+Partitioner: fold labels -> validation index sets, as one CSR.
+
+Drop-in for ``cvmatrix.partitioner.Partitioner`` (reference cvmatrix/partitioner.py:22-107,
+Algorithm 1 of Engstrøm & Jensen 2025).  Same constructor, same ``folds_dict`` (a real
+insertion-ordered dict, key order = first appearance, values = ascending int64 index
+arrays), same ``get_validation_indices`` and the same ``ValueError(f"Fold {fold} not found.")``.
+
+What is new: all index sets live in ONE contiguous int64 buffer (``indices``) delimited by
+``offsets`` — the CSR that ``CVMatrix.set_folds`` uploads to the device once, so a batched
+call can run every fold without any per-fold host work.  The dict values are views into
+that buffer.  Numeric label arrays are partitioned with a stable sort instead of the
+reference's Python loop (0.2-1.5 s at N = 1M); arbitrary hashables use
+the same dict-insertion semantics as the reference.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Hashable
+from typing import Iterable
+
+import numpy as np
+import numpy.typing as npt
+
+
+class Partitioner:
+    """
+    Parameters
+    ----------
+    folds : Iterable of Hashable with N elements
+        Each unique value defines one fold; the indices of the samples carrying it are the
+        validation set of that fold.
+
+    Attributes
+    ----------
+    folds_dict : dict[Hashable, npt.NDArray[np.int_]]
+        key -> ascending int64 indices (views into ``indices``).
+    keys : list
+        Fold keys in first-appearance order (``list(folds_dict)``).
+    offsets : int64 array of P + 1 entries, indices : int64 array of N entries
+        CSR of the validation sets, fold ``k`` owns ``indices[offsets[k]:offsets[k+1]]``.
+    """
+
+    def __init__(self, folds: Iterable[Hashable]) -> None:
+        self.folds_dict: dict[Hashable, npt.NDArray[np.int_]] = {}
+        self._init_folds_dict(folds)
+
+    def get_validation_indices(self, fold: Hashable) -> npt.NDArray[np.int_]:
+        try:
+            return self.folds_dict[fold]
+        except KeyError as e:
+            raise ValueError(f"Fold {fold} not found.") from e
+
+    # ------------------------------------------------------------------------------------------
+    def fold_position(self, fold: Hashable) -> int:
+        """Position of a fold key in the CSR (row of ``offsets``)."""
+        try:
+            return self._pos[fold]
+        except KeyError as e:
+            raise ValueError(f"Fold {fold} not found.") from e
+
+    @property
+    def n_folds(self) -> int:
+        return len(self.keys)
+
+    def csr(self):
+        """(offsets[P+1], indices[N]) as contiguous int64 arrays."""
+        return self.offsets, self.indices
+
+    # ------------------------------------------------------------------------------------------
+    def _init_folds_dict(self, folds: Iterable[Hashable]) -> None:
+        arr = folds if isinstance(folds, np.ndarray) else None
+        if (
+            arr is not None
+            and arr.ndim == 1
+            and arr.dtype.kind in "iufb"
+            and not (arr.dtype.kind == "f" and np.isnan(arr).any())
+        ):
+            keys, offsets, indices = self._partition_numeric(arr)
+        else:
+            keys, offsets, indices = self._partition_hashable(folds)
+        self.keys = keys
+        self.offsets = offsets
+        self.indices = indices
+        self.folds_dict = {k: indices[offsets[p]:offsets[p + 1]] for p, k in enumerate(keys)}
+        self._pos = {k: p for p, k in enumerate(keys)}
+
+    @staticmethod
+    def _partition_numeric(arr: np.ndarray):
+        n = arr.shape[0]
+        if n == 0:
+            return [], np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        _, first, inverse = np.unique(arr, return_index=True, return_inverse=True)
+        inverse = inverse.reshape(-1)
+        order = np.argsort(first, kind="stable")          # unique values by first appearance
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        group = rank[inverse]                              # fold position of every row
+        counts = np.bincount(group, minlength=order.size)
+        offsets = np.zeros(order.size + 1, dtype=np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        small = np.int32 if order.size < 2**31 else np.int64
+        indices = np.argsort(group.astype(small, copy=False), kind="stable").astype(np.int64, copy=False)
+        keys = [arr[i] for i in first[order]]              # numpy scalars, like iterating the array
+        return keys, offsets, np.ascontiguousarray(indices)
+
+    @staticmethod
+    def _partition_hashable(folds: Iterable[Hashable]):
+        buckets: dict[Hashable, list[int]] = {}
+        for i, label in enumerate(folds):
+            rows = buckets.get(label)
+            if rows is None:
+                buckets[label] = [i]
+            else:
+                rows.append(i)
+        keys = list(buckets)
+        offsets = np.zeros(len(keys) + 1, dtype=np.int64)
+        if keys:
+            np.cumsum([len(buckets[k]) for k in keys], out=offsets[1:])
+        indices = np.empty(int(offsets[-1]), dtype=np.int64)
+        for p, k in enumerate(keys):
+            indices[offsets[p]:offsets[p + 1]] = buckets[k]
+        return keys, offsets, indices

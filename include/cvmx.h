@@ -1,0 +1,144 @@
+/*
+ * cvmx.h - C ABI of the B200-native fold-wise training-matrix engine (libcvmx.so).
+ *
+ * This is the drop-in boundary for the hot path of sm00thix/cvmatrix (reference v3.2.1):
+ *     CVMatrix.fit -> Partitioner index sets -> CVMatrix.training_XTX / training_XTY /
+ *     training_XTX_XTY / training_statistics.
+ * The reference has no FFI of its own (pure Python over numpy); the entry points below are
+ * what a binding for this path would call - INTEGRATION.md shows the ctypes stub.  Each
+ * declaration cites the reference code it replaces (file:line under the reference root).
+ *
+ * Conventions
+ *   - every function returns a cvmx_status (0 = CVMX_OK); no exception crosses the boundary;
+ *     cvmx_last_error() gives the message of the last failure on a handle (or on the calling
+ *     thread when no handle exists yet).
+ *   - plain pointers and sizes only.  `mem` says whether the pointers of that call are HOST
+ *     or DEVICE addresses (on the handle's device).  Host pointers are only read/written
+ *     during the call; the library owns its device copies; callers own every output buffer.
+ *   - matrices are row-major.  dtype: 0 = float32, 1 = float64 (all floating-point buffers of
+ *     a handle have the handle's dtype); indices and counts are int64.
+ *   - flags  = center_X | center_Y << 1 | scale_X << 2 | scale_Y << 3
+ *     want   = CVMX_WANT_XTX | CVMX_WANT_XTY | CVMX_WANT_STATS
+ *   - one host thread drives a handle at a time.  All device work of a handle is issued on
+ *     the handle's stream (cvmx_set_stream; default: a private non-blocking stream).
+ *   - there is NO CPU fallback: without a CUDA device cvmx_create fails with CVMX_ERR_CUDA.
+ */
+#ifndef CVMX_H_
+#define CVMX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVMX_VERSION 100 /* 0.1.0 */
+
+typedef struct cvmx_handle cvmx_t;
+
+typedef enum {
+  CVMX_OK = 0,
+  CVMX_ERR_INVALID = 1,    /* bad argument / call order                                   */
+  CVMX_ERR_CUDA = 2,       /* CUDA runtime failure (message in cvmx_last_error)            */
+  CVMX_ERR_NEG_WEIGHT = 3, /* -> ValueError("Weights must be non-negative.")  cvmatrix/cvmatrix.py:1186-1189 */
+  CVMX_ERR_INDEX = 4,      /* validation index outside [-N, N)  -> IndexError (numpy fancy indexing) */
+  CVMX_ERR_NO_Y = 5,       /* XTY wanted but fit() had no Y     cvmatrix/cvmatrix.py:810-811 */
+  CVMX_ERR_NOMEM = 6
+} cvmx_status;
+
+enum { CVMX_F32 = 0, CVMX_F64 = 1 };
+enum { CVMX_HOST = 0, CVMX_DEVICE = 1 };
+enum { CVMX_CENTER_X = 1, CVMX_CENTER_Y = 2, CVMX_SCALE_X = 4, CVMX_SCALE_Y = 8 };
+enum { CVMX_WANT_XTX = 1, CVMX_WANT_XTY = 2, CVMX_WANT_STATS = 4 };
+
+/* per-fold status bits written by the training calls (0 = fine):
+ *   bit 0: weighted and no non-zero weight is left in the training set  (cvmatrix/cvmatrix.py:625-629)
+ *   bit 1: number of non-zero training weights <= ddof                   (cvmatrix/cvmatrix.py:1074-1078)
+ * Whether a bit is an error depends on which statistics the caller's method computes
+ * (cvmatrix/cvmatrix.py:693-699, 722-725); that decision stays with the host wrapper. */
+enum { CVMX_FOLD_NO_NONZERO_W = 1, CVMX_FOLD_NNZ_LE_DDOF = 2 };
+
+int32_t cvmx_version(void);
+const char* cvmx_last_error(const cvmx_t* h); /* h may be NULL */
+
+/* Replaces CVMatrix.__init__ (cvmatrix/cvmatrix.py:157-205).  `resolution` is
+ * np.finfo(dtype).resolution * 10 evaluated by the caller in the model dtype (cvmatrix.py:187). */
+int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof, double resolution,
+                    cvmx_t** out);
+int32_t cvmx_destroy(cvmx_t* h);
+
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all later work. NULL restores
+ * the private stream. */
+int32_t cvmx_set_stream(cvmx_t* h, void* cuda_stream);
+int32_t cvmx_sync(cvmx_t* h);
+
+/*
+ * Replaces CVMatrix.fit (cvmatrix/cvmatrix.py:207-328 -> _init_mats :1153-1191,
+ * _init_weighted_mats :1193-1207, _init_matrix_products :1209-1217, _init_stats :1219-1243).
+ * X is N x K with row pitch ldx (elements), Y is N x M (NULL/M = 0: no responses), w has N
+ * entries (NULL: unweighted).  The library keeps a device copy Z = [X | Y | 0-pad] and w.
+ * It computes   XtWX, XtWY (one weighted Gram pass on FP64 tensor cores),
+ *               sum w (numpy pairwise order), count_nonzero(w),
+ *               column sums of WX, WY, WX.X, WY.Y (numpy order: sequential per column).
+ * [gram_row_begin, gram_row_end) restricts the Gram pass to a row slab (multi-GPU row sharding:
+ * the caller all-reduces cvmx_totals_ptr() across ranks and then calls cvmx_commit_totals);
+ * pass 0, N for the whole matrix.  Moment sums always cover all N rows (their order cannot be
+ * sharded).  Returns CVMX_ERR_NEG_WEIGHT if any weight is negative.
+ */
+int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M,
+                 int64_t ldy, const void* w, int32_t mem, int64_t gram_row_begin, int64_t gram_row_end);
+
+/* Device address and element count of the K x ld [XtWX | XtWY] totals (handle dtype), for an
+ * external all-reduce (NCCL) between cvmx_fit on a row slab and cvmx_commit_totals. */
+int32_t cvmx_totals_ptr(cvmx_t* h, void** dev_ptr, int64_t* count, int64_t* ld);
+int32_t cvmx_commit_totals(cvmx_t* h);
+
+/* Host copies of the public fit attributes XTX, XTY, sum_X, sum_Y, sum_sq_X, sum_sq_Y, sum_w,
+ * num_nonzero_w (cvmatrix/cvmatrix.py:233-314).  Any pointer may be NULL.  Dense outputs:
+ * XTX K*K, XTY K*M, sums K / M.  sum_w is returned as double (exact for float32 too). */
+int32_t cvmx_get_totals(cvmx_t* h, void* XTX, void* XTY, void* sum_X, void* sum_Y, void* sum_sq_X,
+                        void* sum_sq_Y, double* sum_w, int64_t* nnz_w);
+
+/*
+ * Device-resident CSR of validation index sets: replaces the per-fold index arrays of
+ * Partitioner.folds_dict (cvmatrix/partitioner.py:89-107) as consumed by
+ * _get_val_matrices (cvmatrix/cvmatrix.py:924-937).  offsets has P + 1 entries, indices
+ * offsets[P].  Indices may be unsorted / repeated / negative (numpy wrap-around); anything
+ * outside [-N, N) gives CVMX_ERR_INDEX.  Needs a prior cvmx_fit.
+ */
+int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P, int32_t mem);
+
+/*
+ * Batched replacement of _training_matrices / training_statistics for folds
+ * [fold_begin, fold_end) of the CSR (cvmatrix/cvmatrix.py:754-896, 519-574; per fold:
+ * _get_sum_w_train_and_num_nonzero_w_train :589-630, _compute_training_stats :632-752,
+ * _compute_std_divisor :1045-1079, _compute_training_mat_std :1081-1129,
+ * _training_kernel_matrix :943-1010).  With P' = fold_end - fold_begin:
+ *   out_XTX   [P', K, K]   if want & CVMX_WANT_XTX   (else may be NULL)
+ *   out_XTY   [P', K, M]   if want & CVMX_WANT_XTY
+ *   out_stats [P', 4, K+M] rows: mean, std, training column sum, training column sum of squares
+ *                          over the columns of [X | Y]; entries the flags do not define are 0
+ *   out_scal  [P', 2]      sum of training weights, number of non-zero training weights
+ *   out_status[P']         int32 bits CVMX_FOLD_*
+ * out_stats / out_scal / out_status may be NULL.  `mem` applies to all five output pointers.
+ * Centering / scaling of each matrix follows the handle flags exactly as the reference does
+ * (XTX centred iff center_X, XTY centred iff center_X|center_Y, ... :843-864, 1001-1009).
+ */
+int32_t cvmx_training_batch(cvmx_t* h, int64_t fold_begin, int64_t fold_end, uint32_t want, void* out_XTX,
+                            void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status, int32_t mem);
+
+/* Same for ONE ad-hoc validation index set (the reference's per-call signature
+ * training_XTX_XTY(validation_indices), cvmatrix/cvmatrix.py:330-517).  Does not disturb the CSR. */
+int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val_idx, int64_t n_val, int32_t idx_mem, uint32_t want,
+                              void* out_XTX, void* out_XTY, void* out_stats, void* out_scal,
+                              int32_t* out_status, int32_t out_mem);
+
+/* Introspection used by tests / bench: number of kernels launched by this handle so far, and
+ * the padded leading dimension of the device matrices. */
+int64_t cvmx_launch_count(const cvmx_t* h);
+int64_t cvmx_ld(const cvmx_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVMX_H_ */
