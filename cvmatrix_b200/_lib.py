@@ -31,6 +31,8 @@ SIGNATURES = {
     "cvmx_set_folds": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "cvmx_training_batch": (_i32, [_vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_training_indices": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "cvmx_profile_enable": (_i32, [_vp, _i32]),
+    "cvmx_profile_read": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cvmx_launch_count": (_i64, [_vp]),
     "cvmx_ld": (_i64, [_vp]),
 }

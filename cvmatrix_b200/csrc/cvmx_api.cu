@@ -65,6 +65,11 @@ struct cvmx_handle {
   Plan plan;
   bool attr_gram = false, attr_mom = false;
   int64_t launches = 0;
+  // optional per-kernel timing (cvmx_profile_*): event pairs recorded on the handle stream
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;      // pool
+  std::vector<std::pair<int, std::pair<int, int>>> prof_spans;  // (kind, (ev begin, ev end))
+  size_t prof_used = 0;
   std::string err;
 };
 
@@ -83,6 +88,22 @@ int32_t fail(cvmx_t* h, int32_t code, const std::string& msg) {
       return fail(h, e__ == cudaErrorMemoryAllocation ? CVMX_ERR_NOMEM : CVMX_ERR_CUDA,                  \
                   std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
   } while (0)
+
+enum { PROF_STATS = 0, PROF_GRAM = 1, PROF_REDUCE = 2, PROF_KINDS = 3 };
+
+int prof_mark(cvmx_t* h) {
+  if (!h->prof) return -1;
+  if (h->prof_used == h->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    h->prof_ev.push_back(e);
+  }
+  cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+  return (int)h->prof_used++;
+}
+void prof_span(cvmx_t* h, int kind, int a, int b) {
+  if (h->prof && a >= 0 && b >= 0) h->prof_spans.push_back({kind, {a, b}});
+}
 
 inline size_t esz(const cvmx_t* h) { return h->dtype == CVMX_F64 ? 8 : 4; }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
@@ -168,8 +189,11 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   }
   const int64_t grid = (int64_t)pl.units.size() * ntiles;
   if (grid > 0x7fffffffLL) return fail(h, CVMX_ERR_INVALID, "fold batch too large for one launch");
+  const int ev0 = prof_mark(h);
   k_gram<T><<<(unsigned)grid, GTHREADS, smem, h->stream>>>(gp);
   h->launches++;
+  const int ev1 = prof_mark(h);
+  prof_span(h, PROF_GRAM, ev0, ev1);
   CU(h, cudaGetLastError());
   if (!pl.split_folds.empty()) {
     for (size_t s0 = 0; s0 < pl.split_folds.size(); s0 += 65535) {
@@ -178,6 +202,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
                                                                           h->split_folds.as<int32_t>() + s0);
       h->launches++;
     }
+    prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
     CU(h, cudaGetLastError());
   }
   return CVMX_OK;
@@ -306,6 +331,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
   if (h->flags != 0) {
+    const int ev0 = prof_mark(h);
     for (int64_t c0 = 0; c0 < Pn; c0 += 0x7fffffff) {
       const int64_t nb = std::min<int64_t>(0x7fffffff, Pn - c0);
       k_weight_mass<T><<<(unsigned)nb, PW_THREADS, 0, h->stream>>>(
@@ -322,6 +348,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
     int32_t rc = launch_moments<T>(h, mp, Pn, pl.max_rows);
     if (rc) return rc;
+    prof_span(h, PROF_STATS, ev0, prof_mark(h));
   }
   if (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) {
     EpiParams<T> epi;
@@ -464,6 +491,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small})
     b->release();
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return CVMX_OK;
@@ -572,6 +600,32 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val, int64_t n_val, int3
                                      ostatus, out_mem, false)
              : training_impl<float>(h, h->a_off.as<int64_t>(), h->a_idx.as<int64_t>(), off, 0, 1, want, oxx, oxy, ostats, oscal,
                                     ostatus, out_mem, false);
+}
+
+int32_t cvmx_profile_enable(cvmx_t* h, int32_t on) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->prof = on != 0;
+  h->prof_spans.clear();
+  h->prof_used = 0;
+  return CVMX_OK;
+}
+
+int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < PROF_KINDS; ++k) { if (ms) ms[k] = 0; if (count) count[k] = 0; }
+  for (auto& sp : h->prof_spans) {
+    float t = 0;
+    CU(h, cudaEventElapsedTime(&t, h->prof_ev[sp.second.first], h->prof_ev[sp.second.second]));
+    if (ms) ms[sp.first] += t;
+    if (count) count[sp.first] += 1;
+  }
+  h->prof_spans.clear();
+  h->prof_used = 0;
+  return CVMX_OK;
 }
 
 int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }

@@ -60,10 +60,11 @@ struct GramParams {
 };
 
 template <typename T>
-constexpr size_t gram_smem_bytes() {
+__host__ __device__ constexpr size_t gram_smem_bytes() {
   size_t pipe = sizeof(T) * ((size_t)2 * GSTAGES * GBK * GramCfg<T>::PITCH + (size_t)GSTAGES * GBK);
   size_t stage = sizeof(T) * (size_t)GB * GramCfg<T>::CPITCH;
-  return pipe > stage ? pipe : stage;
+  size_t body = (pipe > stage ? pipe : stage);
+  return (body + 15) / 16 * 16 + 2 * GSTAGES * sizeof(uint64_t);   // + full / empty mbarriers at the end
 }
 
 // Epilogue of one 128 x 128 tile.
@@ -175,18 +176,22 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
   }
 }
 
+// Main kernel.  Data movement is done by the TMA engine: per pipeline stage, the 32 lanes of warp 0 each issue
+// one 1-KB bulk async copy (cp.async.bulk, SASS UBLKCP) of a gathered row segment - 16 rows x {A block, B block} -
+// plus an 8-byte cp.async of the row weight, all completing on the stage's "full" mbarrier.  The eight compute
+// warps wait on that barrier, run 4 x 32 DMMA.8x8x4 on the stage and release it through the "empty" mbarrier;
+// there is no block-wide barrier in the main loop.  Row indices are fetched one stage ahead of their use.
 template <typename T>
 __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int PITCH = GramCfg<T>::PITCH;
   typedef typename GramCfg<T>::vec2 vec2;
-  constexpr int EPC = 16 / sizeof(T);        // elements per 16-byte chunk
-  constexpr int CPR = GB / EPC;              // chunks per staged row segment
-  constexpr int LOADS = GBK * CPR / GTHREADS;
 
   T* sA = reinterpret_cast<T*>(smem_raw);
   T* sB = sA + (size_t)GSTAGES * GBK * PITCH;
   T* sW = sB + (size_t)GSTAGES * GBK * PITCH;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + gram_smem_bytes<T>() - 2 * GSTAGES * sizeof(uint64_t));
+  uint64_t* empty = full + GSTAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
@@ -196,39 +201,52 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
   const int bi = tl.x, bj = tl.y;
   const bool diag = bi == bj;
   const int64_t ld = p.ld;
-  const int64_t nk = (unit.row_end - unit.row_begin + GBK - 1) / GBK;
+  const int64_t nrows = unit.row_end - unit.row_begin;
+  const int64_t nk = (nrows + GBK - 1) / GBK;
 
-  auto load_stage = [&](int64_t kt) {
-    if (kt < nk) {
-      const int slot = (int)(kt % GSTAGES);
-      const int64_t k0 = unit.row_begin + kt * GBK;
-#pragma unroll
-      for (int j = 0; j < LOADS; ++j) {
-        const int c = tid + j * GTHREADS;
-        const int r = c / CPR, ch = c % CPR;
-        const int64_t pos = k0 + r;
-        const bool ok = pos < unit.row_end;
-        const int64_t grow = ok ? (p.indices ? p.indices[pos] : pos) : 0;
-        const T* src = p.Z + grow * ld;
-        const int64_t colA = (int64_t)bi * GB + ch * EPC;
-        const bool okA = ok && colA < ld;
-        cp_async16(sA + ((size_t)slot * GBK + r) * PITCH + ch * EPC, okA ? src + colA : p.Z, okA ? 16 : 0);
-        if (!diag) {
-          const int64_t colB = (int64_t)bj * GB + ch * EPC;
-          const bool okB = ok && colB < ld;
-          cp_async16(sB + ((size_t)slot * GBK + r) * PITCH + ch * EPC, okB ? src + colB : p.Z, okB ? 16 : 0);
-        }
-      }
-      if (tid < GBK) {
-        const int64_t pos = k0 + tid;
-        const bool ok = pos < unit.row_end;
-        const int64_t grow = ok ? (p.indices ? p.indices[pos] : pos) : 0;
-        if (sizeof(T) == 8) cp_async8(sW + slot * GBK + tid, p.w + grow, ok ? 8 : 0);
-        else cp_async4(sW + slot * GBK + tid, p.w + grow, ok ? 4 : 0);
-      }
-    }
-    cp_async_commit();
+  if (tid == 0) {
+    for (int s = 0; s < GSTAGES; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, GTHREADS / 32); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer state (warp 0): lane -> (row r = lane % 16, operand o = lane / 16) -------------------
+  const int pr = lane & 15, po = lane >> 4;
+  const int64_t pcol = (int64_t)(po ? bj : bi) * GB;
+  const unsigned pbytes = (unsigned)(min((int64_t)GB, ld - pcol) * (int64_t)sizeof(T));   // > 0: tiles start inside ld
+  auto fetch_row = [&](int64_t kt) -> int64_t {   // global row of this lane's row in stage kt, -1 if none
+    const int64_t pos = unit.row_begin + kt * GBK + pr;
+    if (kt >= nk || pos >= unit.row_end) return -1;
+    return p.indices ? p.indices[pos] : pos;
   };
+  auto issue = [&](int64_t kt, int64_t grow) {    // warp 0 only, all lanes
+    if (kt >= nk) return;
+    const int slot = (int)(kt % GSTAGES);
+    const unsigned round = (unsigned)(kt / GSTAGES);
+    if (round > 0) mbar_wait(empty + slot, (round & 1) ^ 1);
+    const int rows = (int)min((int64_t)GBK, nrows - kt * GBK);
+    if (lane == 0) {
+      const unsigned a_bytes = (unsigned)(min((int64_t)GB, ld - (int64_t)bi * GB) * (int64_t)sizeof(T));
+      const unsigned b_bytes = diag ? 0u : (unsigned)(min((int64_t)GB, ld - (int64_t)bj * GB) * (int64_t)sizeof(T));
+      mbar_arrive_expect_tx(full + slot, (unsigned)rows * (a_bytes + b_bytes));
+    }
+    if (grow >= 0 && !(diag && po)) {
+      T* dst = (po ? sB : sA) + ((size_t)slot * GBK + pr) * PITCH;
+      bulk_g2s(dst, p.Z + grow * ld + pcol, pbytes, full + slot);
+    }
+    if (po == 0) {
+      if (sizeof(T) == 8) cp_async8(sW + slot * GBK + pr, p.w + (grow >= 0 ? grow : 0), grow >= 0 ? 8 : 0);
+      else cp_async4(sW + slot * GBK + pr, p.w + (grow >= 0 ? grow : 0), grow >= 0 ? 4 : 0);
+    }
+    cp_async_mbar_arrive_noinc(full + slot);
+  };
+
+  int64_t next_row = -1;
+  if (warp == 0) {
+#pragma unroll 1
+    for (int s = 0; s < GSTAGES - 1; ++s) issue(s, fetch_row(s));
+    next_row = fetch_row(GSTAGES - 1);
+  }
 
   double acc[8][4][2];
 #pragma unroll
@@ -236,42 +254,73 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
 
-#pragma unroll
-  for (int s = 0; s < GSTAGES - 1; ++s) load_stage(s);
-
+#pragma unroll 1
   for (int64_t kt = 0; kt < nk; ++kt) {
-    cp_async_wait<GSTAGES - 2>();
-    __syncthreads();
-    load_stage(kt + GSTAGES - 1);
+    if (warp == 0) {
+      issue(kt + GSTAGES - 1, next_row);
+      next_row = fetch_row(kt + GSTAGES);
+    }
     const int slot = (int)(kt % GSTAGES);
+    mbar_wait(full + slot, (unsigned)(kt / GSTAGES) & 1);
     const T* a_base = sA + (size_t)slot * GBK * PITCH + wm * 64 + 2 * g;
     const T* b_base = (diag ? sA : sB) + (size_t)slot * GBK * PITCH + wn * 32 + 2 * g;
     const T* w_base = sW + slot * GBK;
+    const int rows = (int)min((int64_t)GBK, nrows - kt * GBK);
+    if (rows == GBK) {
 #pragma unroll
-    for (int kk = 0; kk < GBK / 4; ++kk) {
-      const int k = kk * 4 + q;
-      const T wv = w_base[k];
-      double a[8], b[4];
+      for (int kk = 0; kk < GBK / 4; ++kk) {
+        const int k = kk * 4 + q;
+        const T wv = w_base[k];
+        double a[8], b[4];
 #pragma unroll
-      for (int tp = 0; tp < 4; ++tp) {
-        const vec2 v = *reinterpret_cast<const vec2*>(a_base + k * PITCH + tp * 16);
-        a[2 * tp] = (double)Rn<T>::mul(v.x, wv);       // rn(w*x) in the model dtype == WX of the reference
-        a[2 * tp + 1] = (double)Rn<T>::mul(v.y, wv);
+        for (int tp = 0; tp < 4; ++tp) {
+          const vec2 v = *reinterpret_cast<const vec2*>(a_base + k * PITCH + tp * 16);
+          a[2 * tp] = (double)Rn<T>::mul(v.x, wv);       // rn(w*x) in the model dtype == WX of the reference
+          a[2 * tp + 1] = (double)Rn<T>::mul(v.y, wv);
+        }
+#pragma unroll
+        for (int up = 0; up < 2; ++up) {
+          const vec2 v = *reinterpret_cast<const vec2*>(b_base + k * PITCH + up * 16);
+          b[2 * up] = (double)v.x;
+          b[2 * up + 1] = (double)v.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
       }
+    } else {
+      // tail stage: rows past the end of the unit were never copied - feed exact zeros instead
+#pragma unroll 1
+      for (int kk = 0; kk * 4 < rows; ++kk) {
+        const int k = kk * 4 + q;
+        const bool ok = k < rows;
+        const T wv = ok ? w_base[k] : T(0);
+        double a[8], b[4];
 #pragma unroll
-      for (int up = 0; up < 2; ++up) {
-        const vec2 v = *reinterpret_cast<const vec2*>(b_base + k * PITCH + up * 16);
-        b[2 * up] = (double)v.x;
-        b[2 * up + 1] = (double)v.y;
+        for (int tp = 0; tp < 4; ++tp) {
+          vec2 v; v.x = T(0); v.y = T(0);
+          if (ok) v = *reinterpret_cast<const vec2*>(a_base + k * PITCH + tp * 16);
+          a[2 * tp] = ok ? (double)Rn<T>::mul(v.x, wv) : 0.0;
+          a[2 * tp + 1] = ok ? (double)Rn<T>::mul(v.y, wv) : 0.0;
+        }
+#pragma unroll
+        for (int up = 0; up < 2; ++up) {
+          vec2 v; v.x = T(0); v.y = T(0);
+          if (ok) v = *reinterpret_cast<const vec2*>(b_base + k * PITCH + up * 16);
+          b[2 * up] = (double)v.x;
+          b[2 * up + 1] = (double)v.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
       }
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);
   }
-  cp_async_wait<0>();
-  __syncthreads();
+  __syncthreads();   // every stage consumed by every warp: the ring can be reused as the epilogue tile
 
   if (unit.nsplit == 1) {
     gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
@@ -292,7 +341,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
 template <typename T>
 __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T> p, const int32_t* __restrict__ fold_units,
                                                              const int32_t* __restrict__ fold_list) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const int fold = fold_list[blockIdx.y];

@@ -280,90 +280,124 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
   finalize_column<T>(p, f, c, s, q);
 }
 
-// ---- long folds: cp.async ring feeds one consumer warp that owns 32 sequential column chains ------
-// The chain (one dependent DADD per row, ~8 cycles on B200) is the critical path; all four warps keep
-// MOM_STAGES x MOM_ROWS gathered row segments in flight so the consumer never waits on HBM.
+// ---- long folds: producer warps (cp.async) feed one consumer warp that owns 32 sequential column chains ----
+// The chain (one dependent DADD per row and column, 8 cycles on B200) is the critical path.  Two producer warps
+// gather 32 rows per stage with 16-byte cp.async (LDGSTS) - per-row bulk copies of 256 B are TMA-issue-bound at
+// this granularity, measured - into an MOM_STAGES-deep ring, each lane signalling the stage's mbarrier when its
+// copies land (cp.async.mbarrier.arrive.noinc).  Producers run ahead of the consumer by the ring depth and fetch
+// row indices one group of stages early, so neither index nor HBM latency is exposed to the chain.
 constexpr int MOM_COLS = 32;
 constexpr int MOM_ROWS = 32;
 constexpr int MOM_STAGES = 8;
-constexpr int MOM_THREADS = 128;
+constexpr int MOM_PRODUCERS = 2;                       // producer warps; each owns MOM_ROWS / 2 rows of a stage
+constexpr int MOM_THREADS = 32 * (1 + MOM_PRODUCERS);
+constexpr int MOM_GROUP = 4;                           // stages whose row indices are fetched together
 
 template <typename T>
 __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   T* sz = reinterpret_cast<T*>(smem_raw);                       // [STAGES][ROWS][COLS]
   T* swt = sz + (size_t)MOM_STAGES * MOM_ROWS * MOM_COLS;        // [STAGES][ROWS]
-  const int tid = threadIdx.x;
+  uint64_t* full = reinterpret_cast<uint64_t*>(swt + MOM_STAGES * MOM_ROWS);
+  uint64_t* empty = full + MOM_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f = blockIdx.y;
   const int64_t c0 = (int64_t)blockIdx.x * MOM_COLS;
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
   const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
-  constexpr int CHUNK = 16 / sizeof(T);               // elements per 16-byte cp.async
-  constexpr int CPR = MOM_COLS / CHUNK;               // chunks per row segment
-  constexpr int PER_THREAD = MOM_ROWS * CPR / MOM_THREADS;
   const int64_t nst = (n + MOM_ROWS - 1) / MOM_ROWS;
 
-  auto issue = [&](int64_t st) {
-    if (st < nst) {
-      const int slot = (int)(st % MOM_STAGES);
-#pragma unroll
-      for (int j = 0; j < PER_THREAD; ++j) {
-        const int cidx = tid + j * MOM_THREADS;
-        const int r = cidx / CPR, ch = cidx % CPR;
-        const int64_t row = st * MOM_ROWS + r;
-        const bool ok = row < n;
-        const int64_t g = ok ? (idx ? idx[row] : row) : 0;
-        cp_async16(sz + ((size_t)slot * MOM_ROWS + r) * MOM_COLS + ch * CHUNK, p.Z + g * p.ld + c0 + ch * CHUNK,
-                   ok ? 16 : 0);
-      }
-      if (tid < MOM_ROWS) {
-        const int64_t row = st * MOM_ROWS + tid;
-        const bool ok = row < n;
-        const int64_t g = ok ? (idx ? idx[row] : row) : 0;
-        if (sizeof(T) == 8) cp_async8(swt + slot * MOM_ROWS + tid, p.w + g, ok ? 8 : 0);
-        else cp_async4(swt + slot * MOM_ROWS + tid, p.w + g, ok ? 4 : 0);
-      }
-    }
-    cp_async_commit();
-  };
+  if (tid == 0) {
+    for (int s = 0; s < MOM_STAGES; ++s) { mbar_init(full + s, 32 * MOM_PRODUCERS); mbar_init(empty + s, 1); }
+    mbar_fence_init();
+  }
+  __syncthreads();
 
-  for (int s = 0; s < MOM_STAGES - 1; ++s) issue(s);
+  if (warp >= 1) {
+    // ---------------- producers ----------------
+    constexpr int PROWS = MOM_ROWS / MOM_PRODUCERS;          // rows of a stage owned by this warp (16)
+    constexpr int EPC = 16 / sizeof(T);                      // elements per 16-byte chunk
+    constexpr int CPR = MOM_COLS / EPC;                      // chunks (lanes) per row segment
+    constexpr int RPI = 32 / CPR;                            // rows covered by one warp-wide cp.async
+    constexpr int ITER = PROWS / RPI;
+    const int pw = warp - 1;
+    const int lr = lane / CPR, lc = lane % CPR;
+    int64_t cur[MOM_GROUP], nxt[MOM_GROUP];
+    auto fetch = [&](int64_t st0, int64_t (&g)[MOM_GROUP]) {     // lane l holds the row of local row (l % PROWS)
+#pragma unroll
+      for (int j = 0; j < MOM_GROUP; ++j) {
+        const int64_t row = (st0 + j) * MOM_ROWS + pw * PROWS + (lane % PROWS);
+        g[j] = row < n ? (idx ? idx[row] : row) : -1;
+      }
+    };
+    fetch(0, cur);
+    for (int64_t st0 = 0; st0 < nst; st0 += MOM_GROUP) {
+      fetch(st0 + MOM_GROUP, nxt);
+#pragma unroll
+      for (int j = 0; j < MOM_GROUP; ++j) {
+        const int64_t st = st0 + j;
+        if (st < nst) {
+          const int slot = (int)(st % MOM_STAGES);
+          const unsigned round = (unsigned)(st / MOM_STAGES);
+          if (round > 0) mbar_wait(empty + slot, (round & 1) ^ 1);
+          T* dst = sz + ((size_t)slot * MOM_ROWS + pw * PROWS) * MOM_COLS;
+#pragma unroll
+          for (int i = 0; i < ITER; ++i) {
+            const int r = lr + i * RPI;
+            const int64_t g = __shfl_sync(0xffffffffu, cur[j], r);
+            cp_async16(dst + r * MOM_COLS + lc * EPC, p.Z + (g >= 0 ? g : 0) * p.ld + c0 + lc * EPC, g >= 0 ? 16 : 0);
+          }
+          if (lane < PROWS) {
+            const int64_t g = cur[j];
+            T* wd = swt + slot * MOM_ROWS + pw * PROWS + lane;
+            if (sizeof(T) == 8) cp_async8(wd, p.w + (g >= 0 ? g : 0), g >= 0 ? 8 : 0);
+            else cp_async4(wd, p.w + (g >= 0 ? g : 0), g >= 0 ? 4 : 0);
+          }
+          cp_async_mbar_arrive_noinc(full + slot);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < MOM_GROUP; ++j) cur[j] = nxt[j];
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ---------------- consumer ----------------
   T s_acc = T(0), q_acc = T(0);
   for (int64_t st = 0; st < nst; ++st) {
-    cp_async_wait<MOM_STAGES - 2>();
-    __syncthreads();                 // stage st landed for every thread; slot (st-1) is free again
-    issue(st + MOM_STAGES - 1);
-    if (tid < 32) {
-      const int slot = (int)(st % MOM_STAGES);
-      const T* zr = sz + (size_t)slot * MOM_ROWS * MOM_COLS + tid;
-      const T* wr = swt + slot * MOM_ROWS;
-      const int rows = (int)min((int64_t)MOM_ROWS, n - st * MOM_ROWS);
-      if (rows == MOM_ROWS) {
-#pragma unroll 8
-        for (int r = 0; r < MOM_ROWS; ++r) {
-          const T z = zr[r * MOM_COLS];
-          const T wz = Rn<T>::mul(z, wr[r]);
-          s_acc = Rn<T>::add(s_acc, wz);
-          q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
-        }
-      } else {
-        for (int r = 0; r < rows; ++r) {
-          const T z = zr[r * MOM_COLS];
-          const T wz = Rn<T>::mul(z, wr[r]);
-          s_acc = Rn<T>::add(s_acc, wz);
-          q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
-        }
+    const int slot = (int)(st % MOM_STAGES);
+    const unsigned round = (unsigned)(st / MOM_STAGES);
+    mbar_wait(full + slot, round & 1);
+    const T* zr = sz + (size_t)slot * MOM_ROWS * MOM_COLS + lane;
+    const T* wr = swt + slot * MOM_ROWS;
+    const int rows = (int)min((int64_t)MOM_ROWS, n - st * MOM_ROWS);
+    if (rows == MOM_ROWS) {
+#pragma unroll
+      for (int r = 0; r < MOM_ROWS; ++r) {
+        const T z = zr[r * MOM_COLS];
+        const T wz = Rn<T>::mul(z, wr[r]);
+        s_acc = Rn<T>::add(s_acc, wz);
+        q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
+      }
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        const T z = zr[r * MOM_COLS];
+        const T wz = Rn<T>::mul(z, wr[r]);
+        s_acc = Rn<T>::add(s_acc, wz);
+        q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);
   }
-  cp_async_wait<0>();
-  if (tid < 32) finalize_column<T>(p, f, c0 + tid, s_acc, q_acc);
+  finalize_column<T>(p, f, c0 + lane, s_acc, q_acc);
 }
 
 template <typename T>
 constexpr size_t moments_pipe_smem() {
-  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MOM_COLS + (size_t)MOM_STAGES * MOM_ROWS);
+  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MOM_COLS + (size_t)MOM_STAGES * MOM_ROWS) + 2 * MOM_STAGES * sizeof(uint64_t);
 }
 
 }  // namespace cvmx

@@ -355,8 +355,13 @@ class CVMatrix:
             status = torch.empty((P,), dtype=torch.int32, device=dev)
             p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
             mem = _lib.DEVICE
-            # run stream-ordered with torch so the freshly allocated outputs are safe to write
-            _lib.check(self._lib.cvmx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), self._h)
+            # run stream-ordered with torch so the freshly allocated outputs are safe to write; the legacy
+            # default stream has no handle to share, so order against it with a full synchronisation instead
+            ts = torch.cuda.current_stream(dev)
+            if ts.cuda_stream:
+                _lib.check(self._lib.cvmx_set_stream(self._h, C.c_void_p(ts.cuda_stream)), self._h)
+            else:
+                ts.synchronize()
         elif out == "numpy":
             XTX = np.empty((P, K, K), dt) if return_XTX else None
             XTY = np.empty((P, K, M), dt) if return_XTY else None

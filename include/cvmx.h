@@ -116,8 +116,8 @@ int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices
  * _training_kernel_matrix :943-1010).  With P' = fold_end - fold_begin:
  *   out_XTX   [P', K, K]   if want & CVMX_WANT_XTX   (else may be NULL)
  *   out_XTY   [P', K, M]   if want & CVMX_WANT_XTY
- *   out_stats [P', 4, K+M] rows: mean, std, training column sum, training column sum of squares
- *                          over the columns of [X | Y]; entries the flags do not define are 0
+ *   out_stats [P', 2, K+M] rows: weighted mean, weighted std of the training set over the columns of
+ *                          [X | Y]; entries the flags do not define are 0
  *   out_scal  [P', 2]      sum of training weights, number of non-zero training weights
  *   out_status[P']         int32 bits CVMX_FOLD_*
  * out_stats / out_scal / out_status may be NULL.  `mem` applies to all five output pointers.
@@ -132,6 +132,13 @@ int32_t cvmx_training_batch(cvmx_t* h, int64_t fold_begin, int64_t fold_end, uin
 int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val_idx, int64_t n_val, int32_t idx_mem, uint32_t want,
                               void* out_XTX, void* out_XTY, void* out_stats, void* out_scal,
                               int32_t* out_status, int32_t out_mem);
+
+/* Per-kernel device timing for bench.py's roofline line: while enabled, CUDA events are recorded on the
+ * handle's stream around the statistics kernels (ms[0]), the Gram kernel (ms[1]) and the split-reduce
+ * kernel (ms[2]); cvmx_profile_read synchronises, returns the accumulated milliseconds and span counts
+ * (arrays of 3) since the last read, and resets them. */
+int32_t cvmx_profile_enable(cvmx_t* h, int32_t on);
+int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count);
 
 /* Introspection used by tests / bench: number of kernels launched by this handle so far, and
  * the padded leading dimension of the device matrices. */
