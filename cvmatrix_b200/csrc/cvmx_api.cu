@@ -190,7 +190,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   const int64_t grid = (int64_t)pl.units.size() * ntiles;
   if (grid > 0x7fffffffLL) return fail(h, CVMX_ERR_INVALID, "fold batch too large for one launch");
   const int ev0 = prof_mark(h);
-  k_gram<T><<<(unsigned)grid, GTHREADS, smem, h->stream>>>(gp);
+  k_gram<T><<<(unsigned)grid, GLAUNCH, smem, h->stream>>>(gp);
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);

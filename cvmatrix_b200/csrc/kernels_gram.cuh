@@ -20,6 +20,19 @@ constexpr int GTHREADS = 256; // 8 warps = 2 (rows) x 4 (cols), warp tile 64 x 3
 constexpr int GACC = 64;      // accumulator doubles per thread
 constexpr int GTILE_ELEMS = GB * GB;
 
+constexpr int GPRODUCERS = 4;                       // producer warps (one warpgroup, one warp per SM sub-partition)
+constexpr int GLAUNCH = GTHREADS + 32 * GPRODUCERS;  // k_gram launch size
+// Register split (setmaxnreg works per warpgroup): the kernel starts at <= 168 registers / thread (3 warps per
+// sub-partition); the producer warpgroup shrinks to 64 and the two compute warpgroups grow to 208.  The grown total
+// must stay within what the CTA was launched with (12 warps * 32 * 168 = 64512 registers) or the second
+// setmaxnreg.inc never completes: 8 * 32 * 208 + 4 * 32 * 64 = 61440.
+constexpr int GREGS_PRODUCER = 64;
+constexpr int GREGS_COMPUTE = 208;
+static_assert(GTHREADS * GREGS_COMPUTE + 32 * GPRODUCERS * GREGS_PRODUCER <= (GTHREADS + 32 * GPRODUCERS) * 168,
+              "setmaxnreg budget exceeds the registers the CTA owns");
+// barrier among the GTHREADS compute threads only (the producer warp has left the kernel by then)
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(GTHREADS) : "memory"); }
+
 template <typename T> struct GramCfg;
 // PITCH: shared-memory row pitch of a staged data-row segment, chosen so that the MMA fragment
 // loads (lane -> row l%4, column pair 2*(l/4)) hit distinct banks: f64 LDS.128 needs pitch/2 = 2 (mod 8)
@@ -98,7 +111,7 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
       *reinterpret_cast<vec2*>(sC + r * CP + cb + 2) = hi;
     }
   }
-  __syncthreads();
+  compute_barrier();
 
   if (e.mode == 1) {
     const bool cX = e.flags & 1, cY = e.flags & 2, sX = e.flags & 4, sY = e.flags & 8;
@@ -132,7 +145,7 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
       gv.x = a[0]; gv.y = a[1];
       *reinterpret_cast<vec2*>(sC + r * CP + c) = gv;
     }
-    __syncthreads();
+    compute_barrier();
   }
 
   const bool wxx = e.want & 1, wxy = e.want & 2;
@@ -176,13 +189,15 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
   }
 }
 
-// Main kernel.  Data movement is done by the TMA engine: per pipeline stage, the 32 lanes of warp 0 each issue
-// one 1-KB bulk async copy (cp.async.bulk, SASS UBLKCP) of a gathered row segment - 16 rows x {A block, B block} -
-// plus an 8-byte cp.async of the row weight, all completing on the stage's "full" mbarrier.  The eight compute
-// warps wait on that barrier, run 4 x 32 DMMA.8x8x4 on the stage and release it through the "empty" mbarrier;
-// there is no block-wide barrier in the main loop.  Row indices are fetched one stage ahead of their use.
+// Main kernel, warp-specialised.  Data movement is done by the TMA engine: per pipeline stage, the 32 lanes of a
+// producer warp (warps 8-11 take the stages round-robin) each issue one 1-KB bulk async copy (cp.async.bulk, SASS UBLKCP) of a gathered row segment
+// - 16 rows x {A block, B block} - plus an 8-byte cp.async of the row weight, all completing on the stage's "full"
+// mbarrier.  The eight compute warps wait on that barrier, run 4 x 32 DMMA.8x8x4 on the stage and release it through
+// the "empty" mbarrier; there is no block-wide barrier in the main loop and no compute warp ever issues a copy
+// (with the producer role on a compute warp the ~1300 issue cycles per stage sat on the critical path: ncu showed
+// 20 % of all samples in the full-barrier wait).  Row indices are fetched one stage ahead of their use.
 template <typename T>
-__global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
+__global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int PITCH = GramCfg<T>::PITCH;
   typedef typename GramCfg<T>::vec2 vec2;
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
     if (kt >= nk || pos >= unit.row_end) return -1;
     return p.indices ? p.indices[pos] : pos;
   };
-  auto issue = [&](int64_t kt, int64_t grow) {    // warp 0 only, all lanes
+  auto issue = [&](int64_t kt, int64_t grow) {    // producer warp only, all lanes
     if (kt >= nk) return;
     const int slot = (int)(kt % GSTAGES);
     const unsigned round = (unsigned)(kt / GSTAGES);
@@ -241,12 +256,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
     cp_async_mbar_arrive_noinc(full + slot);
   };
 
-  int64_t next_row = -1;
-  if (warp == 0) {
+  if (warp >= GTHREADS / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GREGS_PRODUCER));
+    int64_t kt = warp - GTHREADS / 32;
+    int64_t row = fetch_row(kt);
 #pragma unroll 1
-    for (int s = 0; s < GSTAGES - 1; ++s) issue(s, fetch_row(s));
-    next_row = fetch_row(GSTAGES - 1);
+    for (; kt < nk; kt += GPRODUCERS) {
+      const int64_t next_row = fetch_row(kt + GPRODUCERS);
+      issue(kt, row);
+      row = next_row;
+    }
+    cp_async_wait<0>();
+    return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GREGS_COMPUTE));
 
   double acc[8][4][2];
 #pragma unroll
@@ -256,10 +279,6 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
 
 #pragma unroll 1
   for (int64_t kt = 0; kt < nk; ++kt) {
-    if (warp == 0) {
-      issue(kt + GSTAGES - 1, next_row);
-      next_row = fetch_row(kt + GSTAGES);
-    }
     const int slot = (int)(kt % GSTAGES);
     mbar_wait(full + slot, (unsigned)(kt / GSTAGES) & 1);
     const T* a_base = sA + (size_t)slot * GBK * PITCH + wm * 64 + 2 * g;
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram(const GramParams<T> p) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + slot);
   }
-  __syncthreads();   // every stage consumed by every warp: the ring can be reused as the epilogue tile
+  compute_barrier();   // every stage consumed by every compute warp: the ring can be reused as the epilogue tile
 
   if (unit.nsplit == 1) {
     gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
