@@ -50,6 +50,9 @@ struct cvmx_handle {
   double resolution = 0;
   int sm_count = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // side stream for the statistics kernels when they can overlap the Gram kernel (large, row-split folds and fit)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // fitted state
   bool fitted = false, weighted = false;
   int64_t N = 0, K = 0, M = 0, ld = 0;
@@ -161,7 +164,8 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
 }
 
 template <typename T>
-int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const EpiParams<T>& epi) {
+int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const EpiParams<T>& epi,
+                    cudaEvent_t stats_ready = nullptr) {
   const int ntiles = (int)pl.tiles.size();
   if (ntiles == 0 || pl.units.empty()) return CVMX_OK;
   CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
@@ -189,12 +193,15 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   }
   const int64_t grid = (int64_t)pl.units.size() * ntiles;
   if (grid > 0x7fffffffLL) return fail(h, CVMX_ERR_INVALID, "fold batch too large for one launch");
+  const bool all_split = pl.split_folds.size() == pl.fold_units.size();
+  if (stats_ready && !all_split) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));  // fused epilogues read the statistics
   const int ev0 = prof_mark(h);
   k_gram<T><<<(unsigned)grid, GLAUNCH, smem, h->stream>>>(gp);
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
   CU(h, cudaGetLastError());
+  if (stats_ready && all_split) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));
   if (!pl.split_folds.empty()) {
     for (size_t s0 = 0; s0 < pl.split_folds.size(); s0 += 65535) {
       const unsigned ny = (unsigned)std::min<size_t>(65535, pl.split_folds.size() - s0);
@@ -205,6 +212,38 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
     prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
     CU(h, cudaGetLastError());
   }
+  return CVMX_OK;
+}
+
+// Small folds (every fold of the batch has <= SMALL_MAX_ROWS rows): streaming rank-n kernel, no tensor cores.
+template <typename T>
+int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, uint32_t want,
+                     const EpiParams<T>& epi, cudaEvent_t stats_ready) {
+  if (stats_ready) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));
+  SmallParams<T> sp;
+  sp.Z = h->Z.as<T>(); sp.w = h->w.as<T>(); sp.ld = h->ld;
+  sp.offsets = d_off; sp.indices = d_idx; sp.fold0 = f0;
+  sp.epi = epi;
+  sp.quads = (int)((h->K + h->M + 3) / 4);
+  int qpad = 1;
+  while (qpad < sp.quads) qpad <<= 1;
+  if (qpad > STHREADS) return fail(h, CVMX_ERR_INVALID, "small-fold path supports K + M <= 1024 per launch row");
+  sp.rows_per_cta = STHREADS / qpad;
+  const unsigned gx = (unsigned)((h->K + sp.rows_per_cta - 1) / sp.rows_per_cta);
+  const int ev0 = prof_mark(h);
+  for (int64_t c0 = 0; c0 < Pn; c0 += (int64_t)65535 * SMALL_FOLDS) {
+    const int64_t nf = std::min<int64_t>(Pn - c0, (int64_t)65535 * SMALL_FOLDS);
+    SmallParams<T> q = sp;
+    q.fold0 = f0 + c0; q.nfolds = nf;
+    q.epi.stats = epi.stats + (size_t)c0 * 2 * h->ld;
+    q.epi.fs = epi.fs + c0;
+    q.epi.out_xx = epi.out_xx ? epi.out_xx + (size_t)c0 * epi.xx_stride : nullptr;
+    q.epi.out_xy = epi.out_xy ? epi.out_xy + (size_t)c0 * epi.xy_stride : nullptr;
+    k_small_folds<T><<<dim3(gx, (unsigned)((nf + SMALL_FOLDS - 1) / SMALL_FOLDS)), STHREADS, 0, h->stream>>>(q);
+    h->launches++;
+  }
+  prof_span(h, PROF_GRAM, ev0, prof_mark(h));
+  CU(h, cudaGetLastError());
   return CVMX_OK;
 }
 
@@ -230,6 +269,22 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     h->launches++;
   }
   CU(h, cudaGetLastError());
+  return CVMX_OK;
+}
+
+// Fork the statistics work onto the side stream (ordered after everything already queued on the main stream);
+// join_stats() returns the event the consumer of the statistics has to wait for.
+int32_t fork_stats(cvmx_t* h, cudaStream_t* saved) {
+  CU(h, cudaEventRecord(h->ev_fork, h->stream));
+  CU(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+  *saved = h->stream;
+  h->stream = h->aux_stream;
+  return CVMX_OK;
+}
+int32_t join_stats(cvmx_t* h, cudaStream_t saved) {
+  cudaError_t e = cudaEventRecord(h->ev_join, h->aux_stream);
+  h->stream = saved;
+  CU(h, e);
   return CVMX_OK;
 }
 
@@ -270,6 +325,10 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   CU(h, cudaMemsetAsync(h->sumsq_z.p, 0, ld * sz, h->stream));
 
   CU(h, h->pwcols.reserve(4 * sz));
+  // moment chains (4-5 ms at N = 1M: 8 cycles per row and column, unsplittable) run beside the Gram kernel
+  cudaStream_t main_stream;
+  int32_t rc0 = fork_stats(h, &main_stream);
+  if (rc0) return rc0;
   k_weight_mass<T><<<1, PW_THREADS, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
                                                    h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
   h->launches++;
@@ -282,6 +341,8 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
   int32_t rc = launch_moments<T>(h, mp, 1, N);
+  if (rc) { h->stream = main_stream; return rc; }
+  rc = join_stats(h, main_stream);
   if (rc) return rc;
 
   // totals: Gram over the row slab [g0, g1) with identity indexing, raw epilogue into Ttot
@@ -299,6 +360,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
     rc = launch_gram<T>(h, pl, nullptr, epi);
     if (rc) return rc;
   }
+  CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   FitScalars fsc;
   CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -328,6 +390,13 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
   CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
   CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
+  const bool want_mats = (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) != 0;
+  const bool overlap = want_mats && h->flags != 0 && pl.split_folds.size() == (size_t)Pn;
+  cudaStream_t main_stream = h->stream;
+  if (overlap) {
+    int32_t rc = fork_stats(h, &main_stream);
+    if (rc) return rc;
+  }
   CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
   if (h->flags != 0) {
@@ -347,10 +416,14 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
     mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
     int32_t rc = launch_moments<T>(h, mp, Pn, pl.max_rows);
-    if (rc) return rc;
+    if (rc) { h->stream = main_stream; return rc; }
     prof_span(h, PROF_STATS, ev0, prof_mark(h));
   }
-  if (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) {
+  if (overlap) {
+    int32_t rc = join_stats(h, main_stream);
+    if (rc) return rc;
+  }
+  if (want_mats) {
     EpiParams<T> epi;
     epi.mode = 1; epi.flags = h->flags; epi.want = want;
     epi.K = K; epi.M = M; epi.ld = ld;
@@ -358,7 +431,9 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     epi.out_xx = dxx; epi.xx_pitch = K; epi.xx_stride = K * K;
     epi.out_xy = dxy; epi.xy_pitch = M; epi.xy_stride = K * M;
     // the Gram kernel reads fold rows through absolute CSR positions
-    int32_t rc = launch_gram<T>(h, pl, d_idx, epi);
+    int32_t rc = (pl.max_rows <= SMALL_MAX_ROWS && K + M <= 4 * STHREADS)
+                     ? launch_small<T>(h, d_off, d_idx, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
+                     : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr);
     if (rc) return rc;
   }
   return CVMX_OK;
@@ -479,6 +554,14 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
     return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
   }
   h->stream = h->own_stream;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the chain kernels must get SMs ahead of queued Gram CTAs
+  if ((e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
+  }
   *out = h;
   return CVMX_OK;
 }
@@ -492,6 +575,9 @@ int32_t cvmx_destroy(cvmx_t* h) {
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return CVMX_OK;

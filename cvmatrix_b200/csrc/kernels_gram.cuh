@@ -115,35 +115,58 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
 
   if (e.mode == 1) {
     const bool cX = e.flags & 1, cY = e.flags & 2, sX = e.flags & 4, sY = e.flags & 8;
-    const T* mean = e.stats + (size_t)fold * 2 * ld;
-    const T* sdev = mean + ld;
+    const T* __restrict__ mean = e.stats + (size_t)fold * 2 * ld;
+    const T* __restrict__ sdev = mean + ld;
+    const T* __restrict__ Tt = e.Ttot;
     const T sw = (T)e.fs[fold].sw;
-#pragma unroll 1
-    for (int idx = tid; idx < GTILE_ELEMS / 2; idx += GTHREADS) {
-      const int r = idx >> 6, c = (idx & 63) * 2;
-      const int64_t i = (int64_t)bi * GB + r, j = (int64_t)bj * GB + c;
-      if (i >= K || j >= C || (diag && c + 1 < r)) continue;
-      vec2 gv = *reinterpret_cast<const vec2*>(sC + r * CP + c);
-      const vec2 tv = *reinterpret_cast<const vec2*>(e.Ttot + i * ld + j);
+    // thread -> fixed column pair c, rows r0, r0 + 4, ...: the column statistics are loaded once, and the loads of
+    // four rows (totals tile from L2, row mean / std) are issued together so their latency overlaps
+    const int c = (tid & 63) * 2, r0 = tid >> 6;
+    const int64_t j = (int64_t)bj * GB + c;
+    if (j < C) {
       const vec2 mj = *reinterpret_cast<const vec2*>(mean + j);
       const vec2 sj = *reinterpret_cast<const vec2*>(sdev + j);
-      const T mi = mean[i], si = sdev[i];
-      T a[2] = {Rn<T>::sub(tv.x, gv.x), Rn<T>::sub(tv.y, gv.y)};
       const T mjj[2] = {mj.x, mj.y}, sjj[2] = {sj.x, sj.y};
+      const bool isX[2] = {j < K, j + 1 < K};
+      constexpr int U = 4;
+#pragma unroll 1
+      for (int it0 = 0; it0 < GB / 4; it0 += U) {
+        vec2 tv[U];
+        T mi[U], si[U];
+        bool ok[U];
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        if (j + x < K) {
-          if (cX) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi, mjj[x])));
-          if (sX) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si, sjj[x]));
-        } else {
-          if (cX || cY) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi, mjj[x])));
-          if (sX && sY) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si, sjj[x]));
-          else if (sX) a[x] = Rn<T>::div(a[x], si);
-          else if (sY) a[x] = Rn<T>::div(a[x], sjj[x]);
+        for (int u = 0; u < U; ++u) {
+          const int r = r0 + 4 * (it0 + u);
+          const int64_t i = (int64_t)bi * GB + r;
+          ok[u] = i < K && !(diag && c + 1 < r);
+          if (ok[u]) {
+            tv[u] = __ldg(reinterpret_cast<const vec2*>(Tt + i * ld + j));
+            mi[u] = __ldg(mean + i);
+            si[u] = __ldg(sdev + i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          const int r = r0 + 4 * (it0 + u);
+          vec2 gv = *reinterpret_cast<const vec2*>(sC + r * CP + c);
+          T a[2] = {Rn<T>::sub(tv[u].x, gv.x), Rn<T>::sub(tv[u].y, gv.y)};
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (isX[x]) {
+              if (cX) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi[u], mjj[x])));
+              if (sX) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si[u], sjj[x]));
+            } else {
+              if (cX || cY) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi[u], mjj[x])));
+              if (sX && sY) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si[u], sjj[x]));
+              else if (sX) a[x] = Rn<T>::div(a[x], si[u]);
+              else if (sY) a[x] = Rn<T>::div(a[x], sjj[x]);
+            }
+          }
+          gv.x = a[0]; gv.y = a[1];
+          *reinterpret_cast<vec2*>(sC + r * CP + c) = gv;
         }
       }
-      gv.x = a[0]; gv.y = a[1];
-      *reinterpret_cast<vec2*>(sC + r * CP + c) = gv;
     }
     compute_barrier();
   }
@@ -403,6 +426,113 @@ template <typename T>
 __global__ void k_fill(T* __restrict__ p, int64_t n, T v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Small folds (leave-one-out, leave-few-out): the downdate is a rank-n_val update with n_val <= SMALL_MAX_ROWS,
+// so the tensor cores have nothing to do and the fold is bound by writing its K x (K+M) result (2.04 MB at
+// K = 500).  Pure streaming kernel, no shared memory, no barriers: a thread owns output row i and four
+// consecutive columns j..j+3, keeps those four totals in registers and loops over SMALL_FOLDS consecutive
+// folds; per fold it reads the fold's row(s) and statistics (L1 / L2 resident), forms
+//   G_ij = sum_r rn(w_r x_ar) x_br   with (a, b) = (min(i,j), max(i,j)) for the XTX part
+// (first product rounded, then FMAs: bit-identical to numpy for n_val = 1, and exactly symmetric by
+// construction), applies the individually rounded epilogue of gram_epilogue and stores 32 contiguous bytes:
+// a warp writes 1 KB of one output row per store pair.
+// ------------------------------------------------------------------------------------------------------
+constexpr int SMALL_MAX_ROWS = 16;
+constexpr int SMALL_FOLDS = 32;   // folds streamed per thread
+constexpr int STHREADS = 256;     // 2 output rows x 128 column quads per CTA
+
+template <typename T>
+struct SmallParams {
+  const T* Z; const T* w; int64_t ld;
+  const int64_t* offsets; const int64_t* indices; int64_t fold0;   // CSR; folds fold0 .. fold0 + nfolds - 1
+  int64_t nfolds;
+  int quads;                                                        // column quads per output row: ceil((K+M)/4)
+  int rows_per_cta;                                                 // STHREADS / quads_padded
+  EpiParams<T> epi;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(STHREADS, 3) k_small_folds(const SmallParams<T> p) {
+  const EpiParams<T>& e = p.epi;
+  typedef typename GramCfg<T>::vec2 vec2;
+  const int64_t K = e.K, C = e.K + e.M, ld = p.ld;
+  const int qpad = STHREADS / p.rows_per_cta;
+  const int64_t i = (int64_t)blockIdx.x * p.rows_per_cta + threadIdx.x / qpad;
+  const int64_t j = (int64_t)(threadIdx.x % qpad) * 4;
+  const int64_t fbeg = (int64_t)blockIdx.y * SMALL_FOLDS;
+  const int64_t fend = min(p.nfolds, fbeg + SMALL_FOLDS);
+  if (i >= K || j >= C) return;
+  const bool cX = e.flags & 1, cY = e.flags & 2, sX = e.flags & 4, sY = e.flags & 8;
+  const bool wxx = e.want & 1, wxy = e.want & 2;
+  const bool vec_ok = (e.xx_pitch % 2 == 0) && (e.xx_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(e.out_xx) % (2 * sizeof(T)) == 0);
+  if (!((wxx && j < K) || (wxy && j + 3 >= K))) return;
+
+  T tt[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) tt[b] = __ldg(e.Ttot + i * ld + j + b);   // j + 3 < ld (ld % 32 == 0)
+
+  for (int64_t f = fbeg; f < fend; ++f) {
+    const int64_t beg = p.offsets[p.fold0 + f];
+    const int n = (int)(p.offsets[p.fold0 + f + 1] - beg);
+    const T* mean = e.stats + (size_t)f * 2 * ld;
+    const T* sdev = mean + ld;
+    const T mi = __ldg(mean + i), si = __ldg(sdev + i);
+    T mj[4], sj[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { mj[b] = __ldg(mean + j + b); sj[b] = __ldg(sdev + j + b); }
+    const T sw = (T)e.fs[f].sw;
+    T g[4] = {T(0), T(0), T(0), T(0)};
+    for (int r = 0; r < n; ++r) {
+      const int64_t row = p.indices[beg + r];
+      const T wr = __ldg(p.w + row);
+      const T* zr = p.Z + row * ld;
+      const T xi = __ldg(zr + i);
+      const T wxi = Rn<T>::mul(xi, wr);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const T zj = __ldg(zr + j + b);
+        // XTX below the diagonal takes the mirrored product so that out[i][j] == out[j][i] bit for bit
+        const bool swap = (j + b < K) && (j + b < i);
+        const T a = swap ? Rn<T>::mul(zj, wr) : wxi;
+        const T c = swap ? xi : zj;
+        g[b] = (r == 0) ? Rn<T>::mul(a, c) : fma(a, c, g[b]);
+      }
+    }
+    T v[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      T a = Rn<T>::sub(tt[b], g[b]);
+      if (j + b < K) {
+        if (cX) a = Rn<T>::sub(a, Rn<T>::mul(sw, Rn<T>::mul(mi, mj[b])));
+        if (sX) a = Rn<T>::div(a, Rn<T>::mul(si, sj[b]));
+      } else {
+        if (cX || cY) a = Rn<T>::sub(a, Rn<T>::mul(sw, Rn<T>::mul(mi, mj[b])));
+        if (sX && sY) a = Rn<T>::div(a, Rn<T>::mul(si, sj[b]));
+        else if (sX) a = Rn<T>::div(a, si);
+        else if (sY) a = Rn<T>::div(a, sj[b]);
+      }
+      v[b] = a;
+    }
+    T* oxx = e.out_xx + (size_t)f * e.xx_stride + i * e.xx_pitch;
+    T* oxy = e.out_xy + (size_t)f * e.xy_stride + i * e.xy_pitch;
+    if (j + 3 < K && vec_ok) {
+      if (wxx) {
+        vec2 lo, hi;
+        lo.x = v[0]; lo.y = v[1]; hi.x = v[2]; hi.y = v[3];
+        *reinterpret_cast<vec2*>(oxx + j) = lo;
+        *reinterpret_cast<vec2*>(oxx + j + 2) = hi;
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t jj = j + b;
+        if (jj < K) { if (wxx) oxx[jj] = v[b]; }
+        else if (jj < C && wxy) oxy[jj - K] = v[b];
+      }
+    }
+  }
 }
 
 }  // namespace cvmx

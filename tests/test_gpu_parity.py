@@ -232,6 +232,32 @@ def test_loo_stream_matches_oracle():
         assert np.array_equal(out["Y_mean"][f], r.Y_mean) and np.array_equal(out["Y_std"][f], r.Y_std)
 
 
+@pytest.mark.parametrize("n_val", [2, 3, 16, 17, 40])
+@pytest.mark.parametrize("flags", [(True, True, True, True), (False, False, False, False), (True, False, False, True)])
+def test_few_rows_per_fold(n_val, flags):
+    """Leave-few-out around the switch between the streaming rank-n kernel (<= 16 rows) and the DMMA kernel."""
+    from cvmatrix_b200 import CVMatrix
+
+    X, Y, w, _ = make_inputs(1000, 150, 12, 1, seed=n_val)
+    rng = np.random.default_rng(n_val)
+    sets = [rng.choice(1000, size=n_val, replace=False) for _ in range(9)]
+    orc = OracleCVMatrix(*flags)
+    orc.fit(X, Y, w)
+    m = CVMatrix(*flags)
+    m.fit(X, Y, w)
+    m.set_folds(sets)
+    out = m.training_batch()
+    for f, val in enumerate(sets):
+        r = orc.fold(val)
+        assert rel_fro(out["XTX"][f], r.XTX) <= 1e-12 and rel_fro(out["XTY"][f], r.XTY) <= 1e-12
+        assert np.array_equal(out["XTX"][f], out["XTX"][f].T)
+        for name, g in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
+            if g is None:
+                assert out[name] is None
+            else:
+                assert np.array_equal(out[name][f], g)
+
+
 def test_refit_copy_and_public_attributes():
     from cvmatrix_b200 import CVMatrix
 
