@@ -250,7 +250,18 @@ def main():
     _lib.check(lib.cvmx_set_stream(h, C.c_void_p(stream.cuda_stream)), h)
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
+    from cvmatrix_b200 import sharding
+    from cvmatrix_b200.distributed import ShardedFolds
+
+    row_sharded = sharding.use_row_sharding(P, world)
+    sf = ShardedFolds(m) if world > 1 else None
+    outs = dict(XTX=oxx, XTY=oxy, stats=ost, scal=osc, status=oss)
+
     def step():
+        if row_sharded:
+            # few large folds: rows of every fold split across ranks, 2 NCCL all-reduces, owners finish their folds
+            sf.training_batch(0, P, out=outs, row_sharded=True)
+            return
         for c0 in range(f0, f1, chunk):
             c1 = min(f1, c0 + chunk)
             _lib.check(lib.cvmx_training_batch(h, c0, c1, 3, vp(oxx), vp(oxy), vp(ost), vp(osc), vp(oss), _lib.DEVICE), h)
@@ -287,7 +298,7 @@ def main():
     value = P / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (k_gram: DMMA Gram + fused epilogue) on this rank ---------------
-    n_val_total = int(part.offsets[f1] - part.offsets[f0])
+    n_val_total = int(part.offsets[f1] - part.offsets[f0]) if not row_sharded else int(part.offsets[P]) // world
     flops_per_step = 2.0 * n_val_total * K * (K + M)             # full (no symmetry credit), SURVEY.md 8(d)
     bytes_per_step = 2.0 * 8 * K * (K + M) * Pl                  # read total + write result per fold
     gram_ms = prof_ms[1] / max(1, args.steps)                    # all k_gram launches of one step
@@ -374,7 +385,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": f"fold-sharded x{world}",
+            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": (f"rows of each fold sharded x{world} + 2 NCCL all-reduces" if row_sharded else f"fold-sharded x{world}"),
                        "l2_policy": "inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8 else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2",
                        "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

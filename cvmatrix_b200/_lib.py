@@ -31,6 +31,10 @@ SIGNATURES = {
     "cvmx_set_folds": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "cvmx_training_batch": (_i32, [_vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_training_indices": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "cvmx_sharded_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cvmx_sharded_gram_count": (_i64, [_vp, _i64, _i64, _u32]),
+    "cvmx_sharded_gram": (_i32, [_vp, _i64, _i64, _u32, _i32, _i32, _vp]),
+    "cvmx_sharded_finish": (_i32, [_vp, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvmx_profile_enable": (_i32, [_vp, _i32]),
     "cvmx_profile_read": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cvmx_launch_count": (_i64, [_vp]),

@@ -184,6 +184,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   gp.indices = d_indices;
   gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = h->partials.as<double>();
+  gp.raw_out = nullptr; gp.force_partials = 0;
   gp.epi = epi;
   const size_t smem = gram_smem_bytes<T>();
   if (!h->attr_gram) {
@@ -248,7 +249,7 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int6
 }
 
 template <typename T>
-int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows) {
+int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard = 0, int n_col_shards = 1) {
   const size_t smem = moments_pipe_smem<T>();
   if (!h->attr_mom) {
     CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -264,8 +265,12 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
       q.pw_cols = mp.pw_cols ? mp.pw_cols + f0 * 4 : nullptr;
       q.stats = mp.stats + (size_t)f0 * 2 * mp.ld;
     }
-    if (pipe) k_moments_pipe<T><<<dim3((unsigned)(mp.ld / MOM_COLS), ny), MOM_THREADS, smem, h->stream>>>(q);
-    else k_moments_direct<T><<<dim3((unsigned)((mp.ld + 127) / 128), ny), 128, 0, h->stream>>>(q);
+    q.grp0 = col_shard; q.grp_stride = n_col_shards;
+    const int64_t groups = pipe ? mp.ld / MOM_COLS : (mp.ld + 127) / 128;
+    const int64_t mine = groups > col_shard ? (groups - col_shard + n_col_shards - 1) / n_col_shards : 0;
+    if (mine == 0) continue;
+    if (pipe) k_moments_pipe<T><<<dim3((unsigned)mine, ny), MOM_THREADS, smem, h->stream>>>(q);
+    else k_moments_direct<T><<<dim3((unsigned)mine, ny), 128, 0, h->stream>>>(q);
     h->launches++;
   }
   CU(h, cudaGetLastError());
@@ -436,6 +441,159 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
                      : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr);
     if (rc) return rc;
   }
+  return CVMX_OK;
+}
+
+// ---- sharded evaluation (multi-GPU: one handle per rank, collectives done by the caller) -------------------------
+// phase 1: statistics of folds [f0, f1) restricted to column groups col_shard, col_shard + n, ... ; the other
+//          entries of the stats buffer stay zero, so an all-reduce(sum) across ranks assembles the full rows.
+template <typename T>
+int32_t sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int col_shard, int n_col_shards) {
+  const int64_t Pn = f1 - f0, ld = h->ld;
+  const size_t sz = sizeof(T);
+  int64_t max_rows = 0;
+  for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, h->h_off[f + 1] - h->h_off[f]);
+  CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
+  CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
+  CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
+  CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
+  if (h->flags == 0) return CVMX_OK;
+  const int ev0 = prof_mark(h);
+  k_weight_mass<T><<<(unsigned)Pn, PW_THREADS, 0, h->stream>>>(
+      h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, 0,
+      h->ddof, h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>(), h->pwcols.as<T>());
+  h->launches++;
+  CU(h, cudaGetLastError());
+  MomentParams<T> mp;
+  mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
+  mp.offsets = h->d_off.as<int64_t>(); mp.indices = h->d_idx.as<int64_t>(); mp.fold0 = f0; mp.N = h->N;
+  mp.flags = h->flags; mp.resolution = (T)h->resolution;
+  mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+  mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
+  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards);
+  prof_span(h, PROF_STATS, ev0, prof_mark(h));
+  return rc;
+}
+
+// phase 2: raw Gram of row shard `shard` of every fold in [f0, f1) -> out [P'][ntiles][GACC][GTHREADS] f64
+template <typename T>
+int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard, int nshards, double* out) {
+  const int64_t Pn = f1 - f0;
+  Plan pl;
+  plan_tiles(h, want, pl.tiles);
+  const int ntiles = (int)pl.tiles.size();
+  // shard boundaries inside each fold's index range, aligned to the stage size
+  std::vector<int64_t> off2(2 * Pn);
+  int64_t total = 0;
+  for (int64_t f = 0; f < Pn; ++f) {
+    const int64_t beg = h->h_off[f0 + f], n = h->h_off[f0 + f + 1] - beg;
+    const int64_t per = round_up((n + nshards - 1) / nshards, GBK);
+    off2[2 * f] = beg + std::min(n, shard * per);
+    off2[2 * f + 1] = beg + std::min(n, (shard + 1) * per);
+    total += off2[2 * f + 1] - off2[2 * f];
+  }
+  // units: split each fold's shard so the grid fills the SMs in whole waves
+  const int64_t sms = h->sm_count;
+  int64_t best_R = 4096; double best = -1;
+  for (int64_t R = 1024; R <= 4096; R += GBK) {
+    int64_t items = 0;
+    for (int64_t f = 0; f < Pn; ++f) items += std::max<int64_t>(1, (off2[2 * f + 1] - off2[2 * f] + R - 1) / R);
+    items *= ntiles;
+    const double eff = (double)items / (double)(sms * ((items + sms - 1) / sms));
+    if (eff > best + 1e-9) { best = eff; best_R = R; }
+  }
+  pl.fold_units.assign(Pn, 0);
+  for (int64_t f = 0; f < Pn; ++f) {
+    const int64_t beg = off2[2 * f], n = off2[2 * f + 1] - beg;
+    const int64_t ns = std::max<int64_t>(1, (n + best_R - 1) / best_R);
+    const int64_t per = round_up((n + ns - 1) / ns, GBK);
+    pl.fold_units[f] = (int32_t)pl.units.size();
+    pl.split_folds.push_back((int32_t)f);
+    for (int64_t s2 = 0; s2 < ns; ++s2) {
+      GramUnit u;
+      u.row_begin = beg + std::min(n, s2 * per); u.row_end = beg + std::min(n, (s2 + 1) * per);
+      u.fold = (int32_t)f; u.split = (int32_t)s2; u.nsplit = (int32_t)ns; u.part_base = (int32_t)pl.n_partial_units;
+      pl.units.push_back(u);
+    }
+    pl.n_partial_units += ns;
+  }
+  (void)total;
+  CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
+  CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
+  CU(h, h->fold_units.reserve(pl.fold_units.size() * sizeof(int32_t)));
+  CU(h, h->split_folds.reserve(pl.split_folds.size() * sizeof(int32_t)));
+  CU(h, h->partials.reserve((size_t)pl.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
+  CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  GramParams<T> gp;
+  gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = h->d_idx.as<int64_t>();
+  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.partials = h->partials.as<double>(); gp.raw_out = out; gp.force_partials = 1;
+  gp.epi = EpiParams<T>();
+  const size_t smem = gram_smem_bytes<T>();
+  if (!h->attr_gram) {
+    CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(h, cudaFuncSetAttribute(k_gram_reduce<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->attr_gram = true;
+  }
+  const int ev0 = prof_mark(h);
+  k_gram<T><<<(unsigned)(pl.units.size() * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+  h->launches++;
+  const int ev1 = prof_mark(h);
+  prof_span(h, PROF_GRAM, ev0, ev1);
+  k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  h->launches++;
+  prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
+  CU(h, cudaGetLastError());
+  return CVMX_OK;
+}
+
+// phase 3: epilogue of folds [f0, f1) from (all-reduced) raw Grams in the fragment layout of phase 2; `first` is
+// the fold of the batch that gram[0] belongs to (a rank may finish only the folds it owns)
+template <typename T>
+int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy) {
+  const int64_t Pn = f1 - f0;
+  if (Pn <= 0) return CVMX_OK;
+  Plan pl;
+  plan_tiles(h, want, pl.tiles);
+  const int ntiles = (int)pl.tiles.size();
+  pl.fold_units.assign(f1 - batch_f0, 0);
+  for (int64_t f = batch_f0; f < f1; ++f) {
+    GramUnit u;
+    u.row_begin = u.row_end = 0; u.fold = (int32_t)(f - batch_f0); u.split = 0; u.nsplit = 1; u.part_base = (int32_t)(f - batch_f0);
+    pl.fold_units[f - batch_f0] = (int32_t)pl.units.size();
+    pl.units.push_back(u);
+    if (f >= f0) pl.split_folds.push_back((int32_t)(f - batch_f0));
+  }
+  CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
+  CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
+  CU(h, h->fold_units.reserve(pl.fold_units.size() * sizeof(int32_t)));
+  CU(h, h->split_folds.reserve(pl.split_folds.size() * sizeof(int32_t)));
+  CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  EpiParams<T> epi;
+  epi.mode = 1; epi.flags = h->flags; epi.want = want;
+  epi.K = h->K; epi.M = h->M; epi.ld = h->ld;
+  epi.Ttot = h->Ttot.as<T>(); epi.stats = h->stats.as<T>(); epi.fs = h->fscal.as<FoldScalars>();
+  // outputs are indexed by fold relative to f0
+  epi.out_xx = oxx ? oxx - (f0 - batch_f0) * h->K * h->K : nullptr; epi.xx_pitch = h->K; epi.xx_stride = h->K * h->K;
+  epi.out_xy = oxy ? oxy - (f0 - batch_f0) * h->K * h->M : nullptr; epi.xy_pitch = h->M; epi.xy_stride = h->K * h->M;
+  GramParams<T> gp;
+  gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = nullptr;
+  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.partials = const_cast<double*>(gram); gp.raw_out = nullptr; gp.force_partials = 0;
+  gp.epi = epi;
+  const size_t smem = gram_smem_bytes<T>();
+  const int ev0 = prof_mark(h);
+  k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  h->launches++;
+  prof_span(h, PROF_REDUCE, ev0, prof_mark(h));
+  CU(h, cudaGetLastError());
   return CVMX_OK;
 }
 
@@ -686,6 +844,62 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val, int64_t n_val, int3
                                      ostatus, out_mem, false)
              : training_impl<float>(h, h->a_off.as<int64_t>(), h->a_idx.as<int64_t>(), off, 0, 1, want, oxx, oxy, ostats, oscal,
                                     ostatus, out_mem, false);
+}
+
+int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard, int32_t n_col_shards, void** stats_dev,
+                           int64_t* stats_count) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats: fit first");
+  if (f0 < 0 || f1 > h->P || f0 >= f1 || n_col_shards < 1 || col_shard < 0 || col_shard >= n_col_shards)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats: bad fold range or shard");
+  CU(h, cudaSetDevice(h->device));
+  int32_t rc = h->dtype == CVMX_F64 ? sharded_stats<double>(h, f0, f1, col_shard, n_col_shards)
+                                    : sharded_stats<float>(h, f0, f1, col_shard, n_col_shards);
+  if (stats_dev) *stats_dev = h->stats.p;
+  if (stats_count) *stats_count = (f1 - f0) * 2 * h->ld;
+  return rc;
+}
+
+int64_t cvmx_sharded_gram_count(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want) {
+  if (!h || !h->fitted || f1 <= f0) return 0;
+  std::vector<int2> tiles;
+  plan_tiles(h, want, tiles);
+  return (f1 - f0) * (int64_t)tiles.size() * GACC * GTHREADS;
+}
+
+int32_t cvmx_sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int32_t row_shard, int32_t n_row_shards, double* gram_dev) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_gram: fit first");
+  if (f0 < 0 || f1 > h->P || f0 >= f1 || n_row_shards < 1 || row_shard < 0 || row_shard >= n_row_shards || !gram_dev)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_gram: bad fold range, shard or buffer");
+  if ((want & CVMX_WANT_XTY) && h->M == 0) return fail(h, CVMX_ERR_NO_Y, "Response variables `Y` are not provided.");
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64 ? sharded_gram<double>(h, f0, f1, want, row_shard, n_row_shards, gram_dev)
+                              : sharded_gram<float>(h, f0, f1, want, row_shard, n_row_shards, gram_dev);
+}
+
+int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram_dev, void* oxx,
+                            void* oxy, void* ostats, void* oscal, int32_t* ostatus) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish: fit first");
+  if (batch_f0 < 0 || f0 < batch_f0 || f1 > h->P || f0 > f1 || !gram_dev)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish: bad fold range or buffer");
+  CU(h, cudaSetDevice(h->device));
+  int32_t rc = h->dtype == CVMX_F64 ? sharded_finish<double>(h, batch_f0, f0, f1, want, gram_dev, (double*)oxx, (double*)oxy)
+                                    : sharded_finish<float>(h, batch_f0, f0, f1, want, gram_dev, (float*)oxx, (float*)oxy);
+  if (rc || f1 == f0) return rc;
+  // statistics / scalars of the owned folds (device pointers)
+  const size_t sz = esz(h);
+  const int64_t C = h->K + h->M, d = f0 - batch_f0, Pn = f1 - f0;
+  if (ostats)
+    CU(h, cudaMemcpy2DAsync(ostats, C * sz, h->stats.as<char>() + (size_t)d * 2 * h->ld * sz, h->ld * sz, C * sz, Pn * 2,
+                            cudaMemcpyDeviceToDevice, h->stream));
+  if (oscal || ostatus) {
+    if (h->dtype == CVMX_F64)
+      k_pack_scalars<double><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>() + d, Pn, (double*)oscal, ostatus);
+    else
+      k_pack_scalars<float><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>() + d, Pn, (float*)oscal, ostatus);
+    h->launches++;
+    CU(h, cudaGetLastError());
+  }
+  return CVMX_OK;
 }
 
 int32_t cvmx_profile_enable(cvmx_t* h, int32_t on) {

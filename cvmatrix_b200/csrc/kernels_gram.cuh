@@ -69,6 +69,9 @@ struct GramParams {
   const GramUnit* units;
   const int2* tiles; int ntiles;
   double* partials;        // [n_partial_units][ntiles][GACC][GTHREADS]
+  double* raw_out;         // k_gram_reduce: if set, store the summed fragments here ([fold][ntiles][GACC][GTHREADS])
+                           // instead of running the epilogue (multi-GPU: all-reduced across ranks, then finished)
+  int force_partials;      // k_gram: write partials even for single-unit folds
   EpiParams<T> epi;
 };
 
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
   }
   compute_barrier();   // every stage consumed by every compute warp: the ring can be reused as the epilogue tile
 
-  if (unit.nsplit == 1) {
+  if (unit.nsplit == 1 && !p.force_partials) {
     gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
   } else {
     double* dst = p.partials + ((size_t)(unit.part_base + unit.split) * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
@@ -408,6 +411,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
         acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
         acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
       }
+  }
+  if (p.raw_out) {
+    double* dst = p.raw_out + ((size_t)unit.fold * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dst[((t * 4 + u) * 2 + 0) * GTHREADS + tid] = acc[t][u][0];
+        dst[((t * 4 + u) * 2 + 1) * GTHREADS + tid] = acc[t][u][1];
+      }
+    return;
   }
   gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, tl.x, tl.y);
 }

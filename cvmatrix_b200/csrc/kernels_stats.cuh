@@ -206,6 +206,7 @@ struct MomentParams {
   const FoldScalars* fs;       // per fold (fold mode)
   const T* pw_cols;            // per fold pairwise column sums for K == 1 / M == 1
   T* stats;                    // [P][2][ld]: mean, std
+  int grp0 = 0, grp_stride = 1; // column-group sharding (multi-GPU): block b handles group grp0 + b * grp_stride
 };
 
 template <typename T>
@@ -250,7 +251,7 @@ __device__ __forceinline__ void finalize_column(const MomentParams<T>& p, int64_
 template <typename T>
 __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
   const int64_t f = blockIdx.y;
-  const int64_t c = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t c = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * 128 + threadIdx.x;
   if (c >= p.ld) return;
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   uint64_t* empty = full + MOM_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f = blockIdx.y;
-  const int64_t c0 = (int64_t)blockIdx.x * MOM_COLS;
+  const int64_t c0 = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * MOM_COLS;
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
   const int64_t* idx = p.offsets ? p.indices + beg : nullptr;

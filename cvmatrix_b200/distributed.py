@@ -1,0 +1,86 @@
+"""
+Multi-GPU evaluation of fold batches: one process per GPU (torchrun), every rank holds a fitted CVMatrix on
+the same data, `torch.distributed` (NCCL over NVLink) carries the two small all-reduces of the row-sharded mode.
+See cvmatrix_b200/sharding.py for the sharding rules and include/cvmx.h (cvmx_sharded_*) for the device side.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib, sharding
+from .cvmatrix import CVMatrix
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+class ShardedFolds:
+    """
+    Runs folds ``[f0, f1)`` of ``cvm``'s device CSR across all ranks of ``group``.
+
+    ``training_batch`` returns device tensors for the folds THIS rank owns (a contiguous block, see
+    ``sharding.fold_block``): dict(fold_begin, fold_end, XTX, XTY, stats, scal, status).  Many folds: each rank
+    simply evaluates its block.  Few folds: every rank computes the raw Gram of its row shard of every fold and the
+    moment chains of its column groups; two all-reduces assemble them; each rank then finishes its own folds.
+    """
+
+    def __init__(self, cvm: CVMatrix, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.cvm, self.group, self.dist, self.torch = cvm, group, dist, torch
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dev = torch.device("cuda", cvm.device)
+        self.tdt = torch.float64 if np.dtype(cvm.dtype) == np.float64 else torch.float32
+        self._gram: Optional["torch.Tensor"] = None
+
+    def alloc_outputs(self, n_folds: int):
+        t, K, M = self.torch, self.cvm.K, self.cvm.M or 0
+        return dict(
+            XTX=t.empty((n_folds, K, K), dtype=self.tdt, device=self.dev),
+            XTY=t.empty((n_folds, K, M), dtype=self.tdt, device=self.dev),
+            stats=t.empty((n_folds, 2, K + M), dtype=self.tdt, device=self.dev),
+            scal=t.empty((n_folds, 2), dtype=self.tdt, device=self.dev),
+            status=t.empty((n_folds,), dtype=t.int32, device=self.dev),
+        )
+
+    def training_batch(self, f0: int, f1: int, out: Optional[dict] = None, row_sharded: Optional[bool] = None):
+        """Must be called on a non-default torch stream that the handle has been bound to (cvmx_set_stream), so
+        that library kernels and NCCL collectives are ordered on one stream."""
+        t, cvm = self.torch, self.cvm
+        lib, h = cvm._lib, cvm._h
+        if row_sharded is None:
+            row_sharded = sharding.use_row_sharding(f1 - f0, self.world)
+        o0, o1 = sharding.fold_block(self.rank, self.world, f0, f1)
+        if out is None:
+            out = self.alloc_outputs(max(o1 - o0, 1))
+        vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        if not row_sharded:
+            if o1 > o0:
+                _lib.check(lib.cvmx_training_batch(h, o0, o1, 3, vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]), vp(out["scal"]),
+                                                   vp(out["status"]), _lib.DEVICE), h)
+            return dict(out, fold_begin=o0, fold_end=o1)
+        # ---- few large folds: rows of every fold split across ranks --------------------------------------
+        sp, sc = C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, self.world, C.byref(sp), C.byref(sc)), h)
+        n = lib.cvmx_sharded_gram_count(h, f0, f1, 3)
+        if self._gram is None or self._gram.numel() < n:
+            self._gram = t.empty((n,), dtype=t.float64, device=self.dev)
+        gram = self._gram[:n]
+        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, self.world, vp(gram)), h)
+        if self.world > 1:
+            stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8" if self.tdt == t.float64 else "<f4"), device=self.dev)
+            self.dist.all_reduce(stats, group=self.group)
+            self.dist.all_reduce(gram, group=self.group)
+        _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
+                                           vp(out["scal"]), vp(out["status"])), h)
+        return dict(out, fold_begin=o0, fold_end=o1)

@@ -1,0 +1,40 @@
+"""
+Pure (device-free) sharding arithmetic of the multi-GPU fold path.  The C library applies the same
+rules inside cvmx_sharded_stats / cvmx_sharded_gram (cvmatrix_b200/csrc/cvmx_api.cu); keeping them here
+lets the N > 1 logic be tested on CPU with a gloo process group.
+
+The path shards two ways:
+  * many folds  -> contiguous fold blocks per rank, no collective;
+  * few folds   -> every fold's rows are split across ranks (one all-reduce of the float64 Gram partials),
+                   the sequential per-column moment chains are split by column group (one all-reduce of
+                   the statistics rows, whose foreign entries are zero).
+"""
+
+from __future__ import annotations
+
+GRAM_ROW_ALIGN = 16      # GBK: rows per pipeline stage of k_gram
+MOMENT_GROUP_COLS = 32   # MOM_COLS: columns per moment-chain CTA
+
+
+def fold_block(rank: int, world: int, f0: int, f1: int):
+    """Contiguous block of folds [f0, f1) owned by `rank`."""
+    n = f1 - f0
+    return f0 + rank * n // world, f0 + (rank + 1) * n // world
+
+
+def use_row_sharding(n_folds: int, world: int) -> bool:
+    """Few large folds cannot keep `world` GPUs busy by fold ownership alone."""
+    return world > 1 and n_folds < 4 * world
+
+
+def row_shard(n_rows: int, shard: int, n_shards: int):
+    """[begin, end) positions of `shard` inside a fold's index list (stage-aligned, last shard takes the rest)."""
+    per = -(-n_rows // n_shards)
+    per = -(-per // GRAM_ROW_ALIGN) * GRAM_ROW_ALIGN
+    return min(n_rows, shard * per), min(n_rows, (shard + 1) * per)
+
+
+def column_groups(ld: int, shard: int, n_shards: int, group_cols: int = MOMENT_GROUP_COLS):
+    """Column groups (of `group_cols` columns) whose moment chains `shard` computes."""
+    n_groups = -(-ld // group_cols)
+    return list(range(shard, n_groups, n_shards))

@@ -133,6 +133,30 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val_idx, int64_t n_val, 
                               void* out_XTX, void* out_XTY, void* out_stats, void* out_scal,
                               int32_t* out_status, int32_t out_mem);
 
+/*
+ * Sharded evaluation of a fold batch across several handles (one per GPU / rank).  The path shards two ways
+ * (SURVEY.md 8e): many folds -> give each rank its own fold range with cvmx_training_batch (no collective);
+ * few large folds -> split every fold's ROWS across ranks with the three phases below, the caller doing the two
+ * all-reduces (NCCL) in between.  All pointers are DEVICE pointers; every rank holds the full data and the CSR.
+ *   1. cvmx_sharded_stats : statistics of folds [f0, f1) for column groups col_shard, col_shard + n_col_shards, ...
+ *        (the sequential per-column chains cannot be split by rows, so they are split by columns).  Returns the
+ *        device address / element count (handle dtype) of the [P'][2][ld] buffer: entries of other shards are zero,
+ *        so all-reduce(sum) in place assembles it.  The per-fold scalars are computed redundantly on every rank.
+ *   2. cvmx_sharded_gram  : raw weighted Gram of row shard `row_shard` of every fold -> gram_dev, float64,
+ *        cvmx_sharded_gram_count() elements (internal tile/fragment order); all-reduce(sum) across ranks.
+ *   3. cvmx_sharded_finish: downdate + centering + scaling epilogue for folds [f0, f1) (a sub-range of the batch
+ *        that started at batch_f0 - typically the folds this rank owns) from the reduced Gram; outputs as in
+ *        cvmx_training_batch, indexed from f0.
+ * Replaces, together, the same reference code as cvmx_training_batch.
+ */
+int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard, int32_t n_col_shards, void** stats_dev,
+                           int64_t* stats_count);
+int64_t cvmx_sharded_gram_count(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want);
+int32_t cvmx_sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int32_t row_shard, int32_t n_row_shards,
+                          double* gram_dev);
+int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram_dev,
+                            void* out_XTX, void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, CUDA events are recorded on the
  * handle's stream around the statistics kernels (ms[0]), the Gram kernel (ms[1]) and the split-reduce
  * kernel (ms[2]); cvmx_profile_read synchronises, returns the accumulated milliseconds and span counts

@@ -1,0 +1,121 @@
+"""
+GPU parity at BASELINE.json's full sizes (-m gpu): cfg 2 (N=1M, K=500, M=10, 5 folds), cfg 3 (1000 folds),
+cfg 4 (leave-one-out N=20k), checked two ways:
+
+1. against the numpy oracle running on the box's host cores (whole cfg 2; a sample of folds for cfg 3 / 4):
+   statistics bit-exact; XTX and the joint [XTX | XTY] to relFro <= 1e-12.  Centred XTY alone at N = 1M is
+   pure cancellation residue (entries ~sqrt(N) against raw sums ~N/8): any summation order other than
+   OpenBLAS's own differs from it by ~3-4e-12 there (numpy itself is 1.1e-10 from the
+   exact value), so XTY alone is held to 2e-11 at N = 1M and to 1e-12 elsewhere.
+2. through size-independent properties: the folds of a partition downdate the totals exactly once
+   (sum_f (T - A_f) == T for the un-preprocessed model), results are exactly symmetric, and a leave-one-out
+   downdate of the un-preprocessed model equals T - rn(w x_i) x_j bit for bit.
+"""
+
+import numpy as np
+import pytest
+
+from cvmatrix_oracle import OracleCVMatrix, make_inputs, rel_fro
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+
+
+@pytest.fixture(scope="module")
+def big():
+    X, Y, w, _ = make_inputs(1_000_000, 500, 10, 5)
+    orc = OracleCVMatrix(copy=False)
+    orc.fit(X, Y, w)
+    return X, Y, w, orc
+
+
+def _check_fold(out, pos, r, xty_tol):
+    XTX, XTY = out["XTX"][pos], out["XTY"][pos]
+    joint = np.hstack([XTX, XTY])
+    jref = np.hstack([r.XTX, r.XTY])
+    assert rel_fro(XTX, r.XTX) <= 1e-12, rel_fro(XTX, r.XTX)
+    assert rel_fro(joint, jref) <= 1e-12, rel_fro(joint, jref)
+    assert rel_fro(XTY, r.XTY) <= xty_tol, rel_fro(XTY, r.XTY)
+    assert np.array_equal(XTX, XTX.T)
+    for name, g in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
+        assert np.array_equal(out[name][pos], g), name
+
+
+def test_cfg2_and_cfg3_full_size(big):
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    X, Y, w, orc = big
+    N = X.shape[0]
+    m = CVMatrix(copy=False)
+    m.fit(X, Y, w)
+    assert np.array_equal(m.sum_X, orc.sum_X) and np.array_equal(m.sum_sq_X, orc.sum_sq_X)
+    assert np.array_equal(m.sum_Y, orc.sum_Y) and np.array_equal(m.sum_sq_Y, orc.sum_sq_Y)
+    assert m.sum_w == orc.sum_w and m.num_nonzero_w == orc.nnz_w
+    assert rel_fro(m.XTX, orc.XTX) <= 1e-14 and rel_fro(m.XTY, orc.XTY) <= 1e-14
+
+    # cfg 2: 5 folds, every fold against the oracle
+    part = Partitioner(np.arange(N) % 5)
+    m.set_folds(part)
+    out = m.training_batch()
+    for pos, key in enumerate(part.folds_dict):
+        _check_fold(out, pos, orc.fold(part.get_validation_indices(key)), xty_tol=2e-11)
+
+    # cfg 3: 1000 folds, a sample against the oracle
+    part = Partitioner(np.arange(N) % 1000)
+    m.set_folds(part)
+    sample = [0, 1, 499, 998, 999]
+    keys = list(part.folds_dict)
+    for f in sample:
+        out = m.training_batch(f, f + 1)
+        _check_fold(out, 0, orc.fold(part.get_validation_indices(keys[f])), xty_tol=2e-11)
+
+
+def test_partition_property_full_size(big):
+    """Un-preprocessed model: A_f = T - G_f and the folds partition the rows, so sum_f (T - A_f) == T."""
+    import torch
+
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    X, Y, w, _ = big
+    N = X.shape[0]
+    m = CVMatrix(False, False, False, False, copy=False)
+    m.fit(X, Y, w)
+    T = torch.from_numpy(np.hstack([m.XTX, m.XTY])).cuda()
+    for P in (5, 1000):
+        m.set_folds(Partitioner(np.arange(N) % P))
+        acc = torch.zeros_like(T)
+        for c0 in range(0, P, 250):
+            out = m.training_batch(c0, min(P, c0 + 250), out="torch")
+            acc += (T.unsqueeze(0) - torch.cat([out["XTX"], out["XTY"]], dim=2)).sum(dim=0)
+            assert torch.equal(out["XTX"], out["XTX"].transpose(1, 2))
+        err = (torch.linalg.norm(acc - T) / torch.linalg.norm(T)).item()
+        assert err <= 1e-13, (P, err)
+
+
+def test_cfg4_leave_one_out_full_size():
+    import torch
+
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    N, K, M = 20_000, 500, 10
+    X, Y, w, _ = make_inputs(N, K, M, 1)
+    orc = OracleCVMatrix(copy=False)
+    orc.fit(X, Y, w)
+    m = CVMatrix(copy=False)
+    m.fit(X, Y, w)
+    part = Partitioner(np.arange(N))
+    m.set_folds(part)
+    for f in (0, 1, 7, 9_999, 19_998, 19_999):
+        out = m.training_batch(f, f + 1)
+        _check_fold(out, 0, orc.fold(np.array([f])), xty_tol=1e-12)
+    # a 2000-fold device-resident chunk: exact symmetry and finite values everywhere
+    dev = m.training_batch(4000, 6000, out="torch")
+    assert torch.equal(dev["XTX"], dev["XTX"].transpose(1, 2)) and bool(torch.isfinite(dev["XTX"]).all())
+    # un-preprocessed LOO downdate is T - rn(w x_i) x_j exactly, given our own totals
+    m0 = CVMatrix(False, False, False, False, copy=False)
+    m0.fit(X, Y, w)
+    m0.set_folds(part)
+    out = m0.training_batch(123, 131)
+    for pos, f in enumerate(range(123, 131)):
+        wx = X[f] * w[f]
+        assert np.array_equal(np.triu(out["XTX"][pos]), np.triu(m0.XTX - np.outer(wx, X[f])))
+        assert np.array_equal(out["XTY"][pos], m0.XTY - np.outer(wx, Y[f]))

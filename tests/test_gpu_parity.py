@@ -302,3 +302,52 @@ def test_torch_device_outputs():
     assert dev["XTX"].is_cuda and dev["XTX"].dtype == torch.float64
     assert np.array_equal(dev["XTX"].cpu().numpy(), host["XTX"]) and np.array_equal(dev["XTY"].cpu().numpy(), host["XTY"])
     assert np.array_equal(dev["X_std"].cpu().numpy(), host["X_std"])
+
+
+@pytest.mark.parametrize("n_shards", [1, 3])
+def test_sharded_phases_match_unsharded(n_shards):
+    """Row-sharded Gram + column-sharded statistics + finish (the multi-GPU protocol of cvmx_sharded_*), emulated
+    on one GPU by running the shards one after the other and summing what the all-reduces would sum."""
+    import ctypes as C
+
+    import torch
+
+    from cvmatrix_b200 import CVMatrix, Partitioner, _lib
+    from cvmatrix_b200.distributed import _DevArray
+
+    X, Y, w, folds = make_inputs(40_000, 200, 6, 4, seed=9)
+    m = CVMatrix()
+    m.fit(X, Y, w)
+    m.set_folds(Partitioner(folds))
+    ref = m.training_batch(out="numpy")
+    lib, h = m._lib, m._h
+    P, K, M = 4, 200, 6
+    n = lib.cvmx_sharded_gram_count(h, 0, P, 3)
+    gram = torch.zeros(n, dtype=torch.float64, device="cuda")
+    part = torch.empty_like(gram)
+    stats_sum = None
+    for s in range(n_shards):
+        sp, sc = C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_sharded_stats(h, 0, P, s, n_shards, C.byref(sp), C.byref(sc)), h)
+        _lib.check(lib.cvmx_sharded_gram(h, 0, P, 3, s, n_shards, C.c_void_p(part.data_ptr())), h)
+        m.sync()
+        view = torch.as_tensor(_DevArray(sp.value, sc.value, "<f8"), device="cuda")
+        stats_sum = view.clone() if stats_sum is None else stats_sum + view
+        gram += part
+    view.copy_(stats_sum)  # what all-reduce(sum) leaves in every rank's buffer
+    torch.cuda.synchronize()
+    oxx = torch.empty((2, K, K), dtype=torch.float64, device="cuda")
+    oxy = torch.empty((2, K, M), dtype=torch.float64, device="cuda")
+    ost = torch.empty((2, 2, K + M), dtype=torch.float64, device="cuda")
+    osc = torch.empty((2, 2), dtype=torch.float64, device="cuda")
+    oss = torch.empty((2,), dtype=torch.int32, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    # this "rank" owns folds 2 and 3 of the batch that starts at fold 0
+    _lib.check(lib.cvmx_sharded_finish(h, 0, 2, 4, 3, vp(gram), vp(oxx), vp(oxy), vp(ost), vp(osc), vp(oss)), h)
+    m.sync()
+    for pos, f in enumerate((2, 3)):
+        assert rel_fro(oxx[pos].cpu().numpy(), ref["XTX"][f]) <= 1e-13
+        assert rel_fro(oxy[pos].cpu().numpy(), ref["XTY"][f]) <= 1e-12
+        assert np.array_equal(ost[pos, 0, :K].cpu().numpy(), ref["X_mean"][f][0])
+        assert np.array_equal(ost[pos, 1, K:].cpu().numpy(), ref["Y_std"][f][0])
+        assert osc[pos, 0].item() == ref["sum_w_train"][f] and oss[pos].item() == 0
