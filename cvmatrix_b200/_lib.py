@@ -32,6 +32,7 @@ SIGNATURES = {
     "cvmx_training_batch": (_i32, [_vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_training_indices": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_sharded_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_i64)]),
+    "cvmx_sharded_stats_wait": (_i32, [_vp]),
     "cvmx_sharded_gram_count": (_i64, [_vp, _i64, _i64, _u32]),
     "cvmx_sharded_gram": (_i32, [_vp, _i64, _i64, _u32, _i32, _i32, _vp]),
     "cvmx_sharded_finish": (_i32, [_vp, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),

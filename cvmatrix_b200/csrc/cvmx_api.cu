@@ -218,7 +218,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
 
 // Small folds (every fold of the batch has <= SMALL_MAX_ROWS rows): streaming rank-n kernel, no tensor cores.
 template <typename T>
-int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, uint32_t want,
+int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const int64_t* off, int64_t f0, int64_t Pn, uint32_t want,
                      const EpiParams<T>& epi, cudaEvent_t stats_ready) {
   if (stats_ready) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));
   SmallParams<T> sp;
@@ -240,7 +240,21 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int6
     q.epi.fs = epi.fs + c0;
     q.epi.out_xx = epi.out_xx ? epi.out_xx + (size_t)c0 * epi.xx_stride : nullptr;
     q.epi.out_xy = epi.out_xy ? epi.out_xy + (size_t)c0 * epi.xy_stride : nullptr;
-    k_small_folds<T><<<dim3(gx, (unsigned)((nf + SMALL_FOLDS - 1) / SMALL_FOLDS)), STHREADS, 0, h->stream>>>(q);
+    const dim3 grid(gx, (unsigned)((nf + SMALL_FOLDS - 1) / SMALL_FOLDS));
+    bool loo = true;   // every fold of this launch has exactly one row -> specialised kernel
+    for (int64_t f = f0 + c0; f < f0 + c0 + nf && loo; ++f) loo = (off[f + 1] - off[f]) == 1;
+    if (loo) {
+      const int64_t pos0 = off[f0 + c0];
+      switch (h->flags & 15u) {
+#define CVMX_LOO_CASE(F) case F: k_loo_folds<T, F><<<grid, STHREADS, 0, h->stream>>>(q, pos0); break;
+        CVMX_LOO_CASE(0) CVMX_LOO_CASE(1) CVMX_LOO_CASE(2) CVMX_LOO_CASE(3) CVMX_LOO_CASE(4) CVMX_LOO_CASE(5) CVMX_LOO_CASE(6)
+        CVMX_LOO_CASE(7) CVMX_LOO_CASE(8) CVMX_LOO_CASE(9) CVMX_LOO_CASE(10) CVMX_LOO_CASE(11) CVMX_LOO_CASE(12)
+        CVMX_LOO_CASE(13) CVMX_LOO_CASE(14) CVMX_LOO_CASE(15)
+#undef CVMX_LOO_CASE
+      }
+    } else {
+      k_small_folds<T><<<grid, STHREADS, 0, h->stream>>>(q);
+    }
     h->launches++;
   }
   prof_span(h, PROF_GRAM, ev0, prof_mark(h));
@@ -437,7 +451,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     epi.out_xy = dxy; epi.xy_pitch = M; epi.xy_stride = K * M;
     // the Gram kernel reads fold rows through absolute CSR positions
     int32_t rc = (pl.max_rows <= SMALL_MAX_ROWS && K + M <= 4 * STHREADS)
-                     ? launch_small<T>(h, d_off, d_idx, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
+                     ? launch_small<T>(h, d_off, d_idx, off, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
                      : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr);
     if (rc) return rc;
   }
@@ -456,6 +470,11 @@ int32_t sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int col_shard, int n_co
   CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
   CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
   CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
+  // the chains run on the side stream beside the Gram kernel of phase 2; cvmx_sharded_stats_wait joins them
+  cudaStream_t main_stream;
+  int32_t rc0 = fork_stats(h, &main_stream);
+  if (rc0) return rc0;
+  struct Restore { cvmx_t* h; cudaStream_t s; ~Restore() { cudaEventRecord(h->ev_join, h->aux_stream); h->stream = s; } } restore{h, main_stream};
   CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
   if (h->flags == 0) return CVMX_OK;
@@ -857,6 +876,13 @@ int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard,
   if (stats_dev) *stats_dev = h->stats.p;
   if (stats_count) *stats_count = (f1 - f0) * 2 * h->ld;
   return rc;
+}
+
+int32_t cvmx_sharded_stats_wait(cvmx_t* h) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats_wait: fit first");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  return CVMX_OK;
 }
 
 int64_t cvmx_sharded_gram_count(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want) {

@@ -12,8 +12,8 @@
 
 namespace cvmx {
 
-constexpr int PW_THREADS = 256;  // 2^8 sub-trees of the pairwise recursion per block
-constexpr int PW_LEVELS = 8;
+constexpr int PW_THREADS = 1024;  // 2^10 sub-trees of the pairwise recursion per block
+constexpr int PW_LEVELS = 10;
 
 // Functor over "element i of the reduced vector" for the three quantities numpy sums pairwise.
 template <typename T>
@@ -147,10 +147,22 @@ k_weight_mass(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int6
   T swv = T(0);
   if (weighted) {
     long long nz = 0, neg = 0;
-    for (int64_t i = tid; i < n; i += PW_THREADS) {
-      const T v = w[idx ? idx[i] : i];
-      nz += (v != T(0));
-      neg += (v < T(0));
+    // 8 independent (index -> weight) load chains per trip: the loop is latency-, not bandwidth-bound
+    for (int64_t i0 = tid; i0 < n; i0 += 8 * PW_THREADS) {
+      int64_t r[8];
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = i0 + (int64_t)u * PW_THREADS;
+        r[u] = i < n ? (idx ? idx[i] : i) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = r[u] >= 0 ? w[r[u]] : T(0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        nz += (v[u] != T(0));
+        neg += (v[u] < T(0));
+      }
     }
     if (nz) atomicAdd((unsigned long long*)&s_cnt[0], (unsigned long long)nz);
     if (neg) atomicAdd((unsigned long long*)&s_cnt[1], (unsigned long long)neg);
@@ -281,25 +293,30 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
   finalize_column<T>(p, f, c, s, q);
 }
 
-// ---- long folds: producer warps (cp.async) feed one consumer warp that owns 32 sequential column chains ----
-// The chain (one dependent DADD per row and column, 8 cycles on B200) is the critical path.  Two producer warps
-// gather 32 rows per stage with 16-byte cp.async (LDGSTS) - per-row bulk copies of 256 B are TMA-issue-bound at
-// this granularity, measured - into an MOM_STAGES-deep ring, each lane signalling the stage's mbarrier when its
-// copies land (cp.async.mbarrier.arrive.noinc).  Producers run ahead of the consumer by the ring depth and fetch
-// row indices one group of stages early, so neither index nor HBM latency is exposed to the chain.
+// ---- long folds: one producer warp (cp.async) feeds two consumer warps that own 32 sequential column chains ---
+// The chain - one dependent DADD per row and column, 8 cycles on B200 - is the critical path, and the FP64 pipe
+// of one SM sub-partition issues a warp-wide DADD/DMUL only every ~2 cycles, so the sum chain (DMUL, DADD) and the
+// sum-of-squares chain (DMUL, DMUL, DADD) run in two different warps (two sub-partitions); each stays below the
+// 8-cycle chain latency.  Two producer warps gather 32 rows per stage with coalesced 16-byte cp.async (a warp-wide
+// instruction covers whole row segments; measured alternatives: per-row 256-byte TMA bulk copies are issue-bound,
+// 6.5 ms vs 2.3 ms at cfg 2, and a lane-per-row mapping is sector-request-bound, 7.4 ms) into an MOM_STAGES-deep
+// ring, each lane signalling the stage's mbarrier when its copies land (cp.async.mbarrier.arrive.noinc).  Row byte
+// offsets are computed once per stage and broadcast by shuffle; row indices are fetched a group of stages early.
 constexpr int MOM_COLS = 32;
-constexpr int MOM_ROWS = 32;
-constexpr int MOM_STAGES = 8;
-constexpr int MOM_PRODUCERS = 2;                       // producer warps; each owns MOM_ROWS / 2 rows of a stage
-constexpr int MOM_THREADS = 32 * (1 + MOM_PRODUCERS);
+constexpr int MOM_ROWS = 64;                           // rows per stage: amortises the ~160 cycles of per-stage bookkeeping (ncu)
+constexpr int MOM_STAGES = 4;
+constexpr int MOM_THREADS = 128;                       // warp 0: sum chain, warp 1: sum-of-squares chain, warps 2-3: producers
 constexpr int MOM_GROUP = 4;                           // stages whose row indices are fetched together
+template <typename T> struct MomCfg { static constexpr int PITCH = MOM_COLS + 16 / sizeof(T); };  // 16-byte pad per row
 
 template <typename T>
 __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* sz = reinterpret_cast<T*>(smem_raw);                       // [STAGES][ROWS][COLS]
-  T* swt = sz + (size_t)MOM_STAGES * MOM_ROWS * MOM_COLS;        // [STAGES][ROWS]
-  uint64_t* full = reinterpret_cast<uint64_t*>(swt + MOM_STAGES * MOM_ROWS);
+  constexpr int PITCH = MomCfg<T>::PITCH;
+  T* sz = reinterpret_cast<T*>(smem_raw);                       // [STAGES][ROWS][PITCH]
+  T* swt = sz + (size_t)MOM_STAGES * MOM_ROWS * PITCH;           // [STAGES][ROWS]
+  T* sres = swt + MOM_STAGES * MOM_ROWS;                         // [COLS] sum-of-squares hand-over
+  uint64_t* full = reinterpret_cast<uint64_t*>(sres + MOM_COLS);
   uint64_t* empty = full + MOM_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f = blockIdx.y;
@@ -310,20 +327,25 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   const int64_t nst = (n + MOM_ROWS - 1) / MOM_ROWS;
 
   if (tid == 0) {
-    for (int s = 0; s < MOM_STAGES; ++s) { mbar_init(full + s, 32 * MOM_PRODUCERS); mbar_init(empty + s, 1); }
+    for (int s = 0; s < MOM_STAGES; ++s) { mbar_init(full + s, 64); mbar_init(empty + s, 2); }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp >= 1) {
-    // ---------------- producers ----------------
-    constexpr int PROWS = MOM_ROWS / MOM_PRODUCERS;          // rows of a stage owned by this warp (16)
+  T acc = T(0);
+  if (warp >= 2) {
+    // ---------------- producers: warp 2 + pw owns rows [16 pw, 16 pw + 16) of every stage ----------------
+    // A warp-wide cp.async covers RPI whole row segments (coalesced 16-byte chunks); the byte offset of each row is
+    // computed once per stage by the lane that fetched its index and broadcast with a shuffle.
+    constexpr int PROWS = MOM_ROWS / 2;
     constexpr int EPC = 16 / sizeof(T);                      // elements per 16-byte chunk
     constexpr int CPR = MOM_COLS / EPC;                      // chunks (lanes) per row segment
     constexpr int RPI = 32 / CPR;                            // rows covered by one warp-wide cp.async
     constexpr int ITER = PROWS / RPI;
-    const int pw = warp - 1;
+    const int pw = warp - 2;
     const int lr = lane / CPR, lc = lane % CPR;
+    const char* zbase = reinterpret_cast<const char*>(p.Z + c0 + lc * EPC);
+    const long long row_bytes = (long long)p.ld * (long long)sizeof(T);
     int64_t cur[MOM_GROUP], nxt[MOM_GROUP];
     auto fetch = [&](int64_t st0, int64_t (&g)[MOM_GROUP]) {     // lane l holds the row of local row (l % PROWS)
 #pragma unroll
@@ -342,15 +364,15 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
           const int slot = (int)(st % MOM_STAGES);
           const unsigned round = (unsigned)(st / MOM_STAGES);
           if (round > 0) mbar_wait(empty + slot, (round & 1) ^ 1);
-          T* dst = sz + ((size_t)slot * MOM_ROWS + pw * PROWS) * MOM_COLS;
+          const int64_t g = cur[j];
+          const long long my_off = g >= 0 ? g * row_bytes : -1;   // byte offset of "my" row, -1: past the end
+          T* dst = sz + ((size_t)slot * MOM_ROWS + pw * PROWS + lr) * PITCH + lc * EPC;
 #pragma unroll
           for (int i = 0; i < ITER; ++i) {
-            const int r = lr + i * RPI;
-            const int64_t g = __shfl_sync(0xffffffffu, cur[j], r);
-            cp_async16(dst + r * MOM_COLS + lc * EPC, p.Z + (g >= 0 ? g : 0) * p.ld + c0 + lc * EPC, g >= 0 ? 16 : 0);
+            const long long off = __shfl_sync(0xffffffffu, my_off, lr + i * RPI);
+            cp_async16(dst + (size_t)i * RPI * PITCH, zbase + (off >= 0 ? off : 0), off >= 0 ? 16 : 0);
           }
           if (lane < PROWS) {
-            const int64_t g = cur[j];
             T* wd = swt + slot * MOM_ROWS + pw * PROWS + lane;
             if (sizeof(T) == 8) cp_async8(wd, p.w + (g >= 0 ? g : 0), g >= 0 ? 8 : 0);
             else cp_async4(wd, p.w + (g >= 0 ? g : 0), g >= 0 ? 4 : 0);
@@ -362,43 +384,50 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
       for (int j = 0; j < MOM_GROUP; ++j) cur[j] = nxt[j];
     }
     cp_async_wait<0>();
-    return;
-  }
-
-  // ---------------- consumer ----------------
-  T s_acc = T(0), q_acc = T(0);
-  for (int64_t st = 0; st < nst; ++st) {
-    const int slot = (int)(st % MOM_STAGES);
-    const unsigned round = (unsigned)(st / MOM_STAGES);
-    mbar_wait(full + slot, round & 1);
-    const T* zr = sz + (size_t)slot * MOM_ROWS * MOM_COLS + lane;
-    const T* wr = swt + slot * MOM_ROWS;
-    const int rows = (int)min((int64_t)MOM_ROWS, n - st * MOM_ROWS);
-    if (rows == MOM_ROWS) {
+  } else {
+    // ---------------- consumers: warp 0 sums rn(w z), warp 1 sums rn(rn(w z) z) ----------------
+    int slot = 0;
+    unsigned parity = 0;
+    int64_t left = n;
+    const T* zr = sz + lane;
+    const T* wr = swt;
+    for (int64_t st = 0; st < nst; ++st) {
+      mbar_wait(full + slot, parity);
+      if (left >= MOM_ROWS) {
+        if (warp == 0) {
 #pragma unroll
-      for (int r = 0; r < MOM_ROWS; ++r) {
-        const T z = zr[r * MOM_COLS];
-        const T wz = Rn<T>::mul(z, wr[r]);
-        s_acc = Rn<T>::add(s_acc, wz);
-        q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
+          for (int r = 0; r < MOM_ROWS; ++r) acc = Rn<T>::add(acc, Rn<T>::mul(zr[r * PITCH], wr[r]));
+        } else {
+#pragma unroll
+          for (int r = 0; r < MOM_ROWS; ++r) {
+            const T z = zr[r * PITCH];
+            acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::mul(z, wr[r]), z));
+          }
+        }
+      } else {
+        for (int r = 0; r < (int)left; ++r) {
+          const T z = zr[r * PITCH];
+          const T wz = Rn<T>::mul(z, wr[r]);
+          acc = Rn<T>::add(acc, warp == 0 ? wz : Rn<T>::mul(wz, z));
+        }
       }
-    } else {
-      for (int r = 0; r < rows; ++r) {
-        const T z = zr[r * MOM_COLS];
-        const T wz = Rn<T>::mul(z, wr[r]);
-        s_acc = Rn<T>::add(s_acc, wz);
-        q_acc = Rn<T>::add(q_acc, Rn<T>::mul(wz, z));
-      }
+      left -= MOM_ROWS;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+      zr += MOM_ROWS * PITCH;
+      wr += MOM_ROWS;
+      if (++slot == MOM_STAGES) { slot = 0; parity ^= 1; zr = sz + lane; wr = swt; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + slot);
+    if (warp == 1) sres[lane] = acc;
   }
-  finalize_column<T>(p, f, c0 + lane, s_acc, q_acc);
+  __syncthreads();
+  if (warp == 0) finalize_column<T>(p, f, c0 + lane, acc, sres[lane]);
 }
 
 template <typename T>
 constexpr size_t moments_pipe_smem() {
-  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MOM_COLS + (size_t)MOM_STAGES * MOM_ROWS) + 2 * MOM_STAGES * sizeof(uint64_t);
+  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MomCfg<T>::PITCH + (size_t)MOM_STAGES * MOM_ROWS + MOM_COLS) +
+         2 * MOM_STAGES * sizeof(uint64_t);
 }
 
 }  // namespace cvmx

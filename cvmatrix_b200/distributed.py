@@ -77,6 +77,7 @@ class ShardedFolds:
             self._gram = t.empty((n,), dtype=t.float64, device=self.dev)
         gram = self._gram[:n]
         _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, self.world, vp(gram)), h)
+        _lib.check(lib.cvmx_sharded_stats_wait(h), h)   # the chains ran on a side stream beside the Gram kernel
         if self.world > 1:
             stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8" if self.tdt == t.float64 else "<f4"), device=self.dev)
             self.dist.all_reduce(stats, group=self.group)

@@ -151,6 +151,7 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val_idx, int64_t n_val, 
  */
 int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard, int32_t n_col_shards, void** stats_dev,
                            int64_t* stats_count);
+int32_t cvmx_sharded_stats_wait(cvmx_t* h); /* phase 1 runs on a side stream beside phase 2: call this before touching its result */
 int64_t cvmx_sharded_gram_count(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want);
 int32_t cvmx_sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int32_t row_shard, int32_t n_row_shards,
                           double* gram_dev);

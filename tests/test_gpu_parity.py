@@ -330,6 +330,7 @@ def test_sharded_phases_match_unsharded(n_shards):
         sp, sc = C.c_void_p(), C.c_int64()
         _lib.check(lib.cvmx_sharded_stats(h, 0, P, s, n_shards, C.byref(sp), C.byref(sc)), h)
         _lib.check(lib.cvmx_sharded_gram(h, 0, P, 3, s, n_shards, C.c_void_p(part.data_ptr())), h)
+        _lib.check(lib.cvmx_sharded_stats_wait(h), h)
         m.sync()
         view = torch.as_tensor(_DevArray(sp.value, sc.value, "<f8"), device="cuda")
         stats_sum = view.clone() if stats_sum is None else stats_sum + view
