@@ -255,6 +255,11 @@ def main():
 
     row_sharded = sharding.use_row_sharding(P, world)
     sf = ShardedFolds(m) if world > 1 else None
+    emulate = int(os.environ.get("BENCH_EMULATE_SHARDS", "0"))   # profiling aid: rank 0's share of an N-way sharded step
+    if emulate and world == 1:
+        sf = ShardedFolds(m)
+        sf.emulate_shards = emulate
+        row_sharded = True
     outs = dict(XTX=oxx, XTY=oxy, stats=ost, scal=osc, status=oss)
 
     def step():

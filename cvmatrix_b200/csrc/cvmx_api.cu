@@ -51,8 +51,8 @@ struct cvmx_handle {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // side stream for the statistics kernels when they can overlap the Gram kernel (large, row-split folds and fit)
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mass = nullptr;
   // fitted state
   bool fitted = false, weighted = false;
   int64_t N = 0, K = 0, M = 0, ld = 0;
@@ -64,7 +64,7 @@ struct cvmx_handle {
   // ad-hoc index set (cvmx_training_indices)
   DevBuf a_off, a_idx;
   // scratch
-  DevBuf units, tiles, fold_units, split_folds, partials, stats, fscal, pwcols, errflag, out_xx, out_xy, out_small;
+  DevBuf units, tiles, fold_units, split_folds, partials, stats, rawsums, fscal, pwcols, errflag, out_xx, out_xy, out_small;
   Plan plan;
   bool attr_gram = false, attr_mom = false;
   int64_t launches = 0;
@@ -264,12 +264,20 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
 
 template <typename T>
 int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard = 0, int n_col_shards = 1) {
-  const size_t smem = moments_pipe_smem<T>();
   if (!h->attr_mom) {
-    CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)moments_pipe_smem<T>(MOM_STAGES_DEEP)));
     h->attr_mom = true;
   }
   const bool pipe = max_rows >= 128;
+  // few long chains (they overlap a loaded memory system): deep ring, one CTA per SM; many short chains: 4 stages so
+  // that three CTAs share an SM
+  {
+    const int64_t groups0 = mp.ld / MOM_COLS;
+    const int64_t mine0 = groups0 > col_shard ? (groups0 - col_shard + n_col_shards - 1) / n_col_shards : 0;
+    mp.stages = (mine0 * nfolds <= 32 && max_rows >= 4096) ? MOM_STAGES_DEEP : MOM_STAGES;
+  }
+  const size_t smem = moments_pipe_smem<T>(mp.stages);
   for (int64_t f0 = 0; f0 < nfolds; f0 += 65535) {
     const unsigned ny = (unsigned)std::min<int64_t>(65535, nfolds - f0);
     MomentParams<T> q = mp;
@@ -278,6 +286,7 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
       q.fs = mp.fs + f0;
       q.pw_cols = mp.pw_cols ? mp.pw_cols + f0 * 4 : nullptr;
       q.stats = mp.stats + (size_t)f0 * 2 * mp.ld;
+      q.raw = mp.raw ? mp.raw + (size_t)f0 * 2 * mp.ld : nullptr;
     }
     q.grp0 = col_shard; q.grp_stride = n_col_shards;
     const int64_t groups = pipe ? mp.ld / MOM_COLS : (mp.ld + 127) / 128;
@@ -304,6 +313,67 @@ int32_t join_stats(cvmx_t* h, cudaStream_t saved) {
   cudaError_t e = cudaEventRecord(h->ev_join, h->aux_stream);
   h->stream = saved;
   CU(h, e);
+  return CVMX_OK;
+}
+
+// Statistics of folds [f0, f0 + Pn): weight masses (side stream 2) and moment chains (current stream) run
+// concurrently - the chains store raw sums - and k_finalize_stats turns them into means / stds once both are done.
+template <typename T>
+int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, int64_t max_rows,
+                          int col_shard, int n_col_shards) {
+  const size_t sz = sizeof(T);
+  const int64_t ld = h->ld;
+  CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
+  CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
+  CU(h, h->rawsums.reserve((size_t)Pn * 2 * ld * sz));
+  CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
+  CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
+  if (h->flags == 0) return CVMX_OK;
+  const int ev0 = prof_mark(h);
+  // weight masses on side stream 2 (ordered after the memsets above)
+  CU(h, cudaEventRecord(h->ev_mass, h->stream));
+  CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+  for (int64_t c0 = 0; c0 < Pn; c0 += 0x7fffffff) {
+    const int64_t nb = std::min<int64_t>(0x7fffffff, Pn - c0);
+    if (max_rows <= 1024)
+      k_weight_mass<T, PW_LEVELS_SMALL><<<(unsigned)nb, 1 << PW_LEVELS_SMALL, 0, h->aux2_stream>>>(
+          h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
+          h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
+    else
+      k_weight_mass<T, PW_LEVELS_BIG><<<(unsigned)nb, 1 << PW_LEVELS_BIG, 0, h->aux2_stream>>>(
+          h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
+          h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
+    h->launches++;
+  }
+  CU(h, cudaGetLastError());
+  CU(h, cudaEventRecord(h->ev_mass, h->aux2_stream));
+  MomentParams<T> mp;
+  mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
+  mp.offsets = d_off; mp.indices = d_idx; mp.fold0 = f0; mp.N = h->N;
+  mp.flags = h->flags; mp.resolution = (T)h->resolution;
+  mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+  mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
+  mp.raw = h->rawsums.as<T>();
+  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards);
+  if (rc) return rc;
+  CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0));
+  mp.grp0 = 0; mp.grp_stride = 1;
+  if (n_col_shards > 1) {
+    // only this shard's column groups hold sums; the others must stay zero for the all-reduce
+    // (group width of the kernel that produced them)
+  }
+  for (int64_t c0 = 0; c0 < Pn; c0 += 65535) {
+    const unsigned ny = (unsigned)std::min<int64_t>(65535, Pn - c0);
+    MomentParams<T> q = mp;
+    q.fs = mp.fs + c0; q.pw_cols = mp.pw_cols + c0 * 4; q.stats = mp.stats + (size_t)c0 * 2 * ld; q.raw = mp.raw + (size_t)c0 * 2 * ld;
+    q.grp0 = col_shard; q.grp_stride = n_col_shards;
+    q.stages = (max_rows >= 128) ? MOM_COLS : 128;   // reused as "columns per group" by k_finalize_stats
+    k_finalize_stats<T><<<dim3((unsigned)((ld + 127) / 128), ny), 128, 0, h->stream>>>(q, (int64_t)ny);
+    h->launches++;
+  }
+  CU(h, cudaGetLastError());
+  prof_span(h, PROF_STATS, ev0, prof_mark(h));
   return CVMX_OK;
 }
 
@@ -348,7 +418,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   cudaStream_t main_stream;
   int32_t rc0 = fork_stats(h, &main_stream);
   if (rc0) return rc0;
-  k_weight_mass<T><<<1, PW_THREADS, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
                                                    h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
   h->launches++;
   CU(h, cudaGetLastError());
@@ -396,7 +466,6 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
                   uint32_t want, T* dxx, T* dxy, bool cacheable) {
   const int64_t Pn = f1 - f0;
   if (Pn <= 0) return CVMX_OK;
-  const size_t sz = sizeof(T);
   const int64_t ld = h->ld, K = h->K, M = h->M;
   Plan local;
   Plan& pl = cacheable ? h->plan : local;
@@ -406,9 +475,6 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     plan_units(h, off, f0, f1, (int)pl.tiles.size(), pl);
     pl.fold_begin = f0; pl.fold_end = f1; pl.want = want; pl.csr_version = h->csr_version;
   }
-  CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
-  CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
-  CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
   const bool want_mats = (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) != 0;
   const bool overlap = want_mats && h->flags != 0 && pl.split_folds.size() == (size_t)Pn;
   cudaStream_t main_stream = h->stream;
@@ -416,27 +482,9 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     int32_t rc = fork_stats(h, &main_stream);
     if (rc) return rc;
   }
-  CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
-  CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
-  if (h->flags != 0) {
-    const int ev0 = prof_mark(h);
-    for (int64_t c0 = 0; c0 < Pn; c0 += 0x7fffffff) {
-      const int64_t nb = std::min<int64_t>(0x7fffffff, Pn - c0);
-      k_weight_mass<T><<<(unsigned)nb, PW_THREADS, 0, h->stream>>>(
-          h->Z.as<T>(), h->w.as<T>(), ld, h->N, K, M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
-          h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
-      h->launches++;
-    }
-    CU(h, cudaGetLastError());
-    MomentParams<T> mp;
-    mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
-    mp.offsets = d_off; mp.indices = d_idx; mp.fold0 = f0; mp.N = h->N;
-    mp.flags = h->flags; mp.resolution = (T)h->resolution;
-    mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
-    mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
-    int32_t rc = launch_moments<T>(h, mp, Pn, pl.max_rows);
+  {
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1);
     if (rc) { h->stream = main_stream; return rc; }
-    prof_span(h, PROF_STATS, ev0, prof_mark(h));
   }
   if (overlap) {
     int32_t rc = join_stats(h, main_stream);
@@ -463,36 +511,16 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
 //          entries of the stats buffer stay zero, so an all-reduce(sum) across ranks assembles the full rows.
 template <typename T>
 int32_t sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int col_shard, int n_col_shards) {
-  const int64_t Pn = f1 - f0, ld = h->ld;
-  const size_t sz = sizeof(T);
+  const int64_t Pn = f1 - f0;
   int64_t max_rows = 0;
   for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, h->h_off[f + 1] - h->h_off[f]);
-  CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
-  CU(h, h->stats.reserve((size_t)Pn * 2 * ld * sz));
-  CU(h, h->pwcols.reserve((size_t)Pn * 4 * sz));
   // the chains run on the side stream beside the Gram kernel of phase 2; cvmx_sharded_stats_wait joins them
   cudaStream_t main_stream;
   int32_t rc0 = fork_stats(h, &main_stream);
   if (rc0) return rc0;
-  struct Restore { cvmx_t* h; cudaStream_t s; ~Restore() { cudaEventRecord(h->ev_join, h->aux_stream); h->stream = s; } } restore{h, main_stream};
-  CU(h, cudaMemsetAsync(h->stats.p, 0, (size_t)Pn * 2 * ld * sz, h->stream));
-  CU(h, cudaMemsetAsync(h->fscal.p, 0, Pn * sizeof(FoldScalars), h->stream));
-  if (h->flags == 0) return CVMX_OK;
-  const int ev0 = prof_mark(h);
-  k_weight_mass<T><<<(unsigned)Pn, PW_THREADS, 0, h->stream>>>(
-      h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, 0,
-      h->ddof, h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>(), h->pwcols.as<T>());
-  h->launches++;
-  CU(h, cudaGetLastError());
-  MomentParams<T> mp;
-  mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
-  mp.offsets = h->d_off.as<int64_t>(); mp.indices = h->d_idx.as<int64_t>(); mp.fold0 = f0; mp.N = h->N;
-  mp.flags = h->flags; mp.resolution = (T)h->resolution;
-  mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
-  mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
-  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards);
-  prof_span(h, PROF_STATS, ev0, prof_mark(h));
-  return rc;
+  int32_t rc = launch_fold_stats<T>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, Pn, max_rows, col_shard, n_col_shards);
+  int32_t rc2 = join_stats(h, main_stream);
+  return rc ? rc : rc2;
 }
 
 // phase 2: raw Gram of row shard `shard` of every fold in [f0, f1) -> out [P'][ntiles][GACC][GTHREADS] f64
@@ -734,6 +762,8 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the chain kernels must get SMs ahead of queued Gram CTAs
   if ((e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&h->aux2_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_mass, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
     delete h;
@@ -748,11 +778,13 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
-                    &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->fscal, &h->pwcols,
+                    &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+  if (h->aux2_stream) { cudaStreamSynchronize(h->aux2_stream); cudaStreamDestroy(h->aux2_stream); }
+  if (h->ev_mass) cudaEventDestroy(h->ev_mass);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -12,8 +12,8 @@
 
 namespace cvmx {
 
-constexpr int PW_THREADS = 1024;  // 2^10 sub-trees of the pairwise recursion per block
-constexpr int PW_LEVELS = 10;
+constexpr int PW_LEVELS_BIG = 10;   // 1024 sub-trees of the pairwise recursion per block (long folds, fit)
+constexpr int PW_LEVELS_SMALL = 5;  // one warp per fold (folds of <= 1024 rows)
 
 // Functor over "element i of the reduced vector" for the three quantities numpy sums pairwise.
 template <typename T>
@@ -93,8 +93,9 @@ __device__ T pw_serial(const F& f, int64_t off0, int64_t n0) {
 // Whole-block evaluation of the same tree: thread j walks PW_LEVELS levels down along the bits of j,
 // sums its sub-tree serially, then the sub-tree values are combined bottom-up in exactly the order the
 // recursion would (left + right).  Result is valid in thread 0 (and in s_val[0]).
-template <typename T, typename F>
+template <typename T, int LEVELS, typename F>
 __device__ T block_pairwise(const F& f, int64_t n, T* s_val, unsigned char* s_valid) {
+  constexpr int PW_LEVELS = LEVELS, PW_THREADS = 1 << LEVELS;
   const int tid = threadIdx.x;
   int64_t off = 0, len = n;
   bool owner = true;
@@ -127,12 +128,13 @@ struct FitScalars {  // device-resident fit totals
 // One block per fold (or one block for the whole data set when fit_mode): pairwise weight sum,
 // non-zero count, the derived training scalars, and - for K == 1 / M == 1 - the pairwise column sums.
 //   pw_cols[f][4] = { sum wx, sum wx*x, sum wy, sum wy*y } over the fold rows (only the C == 1 ones are used)
-template <typename T>
-__global__ void __launch_bounds__(PW_THREADS)
+template <typename T, int LEVELS>
+__global__ void __launch_bounds__(1 << LEVELS)
 k_weight_mass(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t N, int64_t K, int64_t M,
               int weighted, const int64_t* __restrict__ offsets, const int64_t* __restrict__ indices,
               int64_t fold0, int fit_mode, int64_t ddof, FitScalars* __restrict__ fit, FoldScalars* __restrict__ fs,
               T* __restrict__ pw_cols) {
+  constexpr int PW_THREADS = 1 << LEVELS;
   __shared__ T s_val[PW_THREADS];
   __shared__ unsigned char s_valid[PW_THREADS];
   __shared__ long long s_cnt[2];
@@ -167,18 +169,18 @@ k_weight_mass(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int6
     if (nz) atomicAdd((unsigned long long*)&s_cnt[0], (unsigned long long)nz);
     if (neg) atomicAdd((unsigned long long*)&s_cnt[1], (unsigned long long)neg);
     PwSrc<T> src{Z, w, idx, ld, 0, 0};
-    swv = block_pairwise<T>(src, n, s_val, s_valid);
+    swv = block_pairwise<T, LEVELS>(src, n, s_val, s_valid);
   }
   T cols[4] = {T(0), T(0), T(0), T(0)};
   if (K == 1) {
     PwSrc<T> a{Z, w, idx, ld, 0, 1}, b{Z, w, idx, ld, 0, 2};
-    cols[0] = block_pairwise<T>(a, n, s_val, s_valid);
-    cols[1] = block_pairwise<T>(b, n, s_val, s_valid);
+    cols[0] = block_pairwise<T, LEVELS>(a, n, s_val, s_valid);
+    cols[1] = block_pairwise<T, LEVELS>(b, n, s_val, s_valid);
   }
   if (M == 1) {
     PwSrc<T> a{Z, w, idx, ld, K, 1}, b{Z, w, idx, ld, K, 2};
-    cols[2] = block_pairwise<T>(a, n, s_val, s_valid);
-    cols[3] = block_pairwise<T>(b, n, s_val, s_valid);
+    cols[2] = block_pairwise<T, LEVELS>(a, n, s_val, s_valid);
+    cols[3] = block_pairwise<T, LEVELS>(b, n, s_val, s_valid);
   }
   __syncthreads();
   if (tid != 0) return;
@@ -219,6 +221,9 @@ struct MomentParams {
   const T* pw_cols;            // per fold pairwise column sums for K == 1 / M == 1
   T* stats;                    // [P][2][ld]: mean, std
   int grp0 = 0, grp_stride = 1; // column-group sharding (multi-GPU): block b handles group grp0 + b * grp_stride
+  T* raw = nullptr;             // [P][2][ld]: if set, store the raw fold sums (s, q) here and leave mean / std to
+                                // k_finalize_stats - the chains then do not depend on the weight-mass kernel
+  int stages = 4;               // ring depth of k_moments_pipe (runtime: few long chains want more bytes in flight)
 };
 
 template <typename T>
@@ -226,6 +231,12 @@ __device__ __forceinline__ void finalize_column(const MomentParams<T>& p, int64_
   const int64_t C = p.K + p.M;
   if (c >= C) return;
   const bool isX = c < p.K;
+  if (p.offsets && p.raw) {  // deferred: k_finalize_stats turns the sums into mean / std once the fold scalars exist
+    T* o = p.raw + (size_t)f * 2 * p.ld;
+    o[c] = s;
+    o[p.ld + c] = q;
+    return;
+  }
   if (p.pw_cols) {
     if (isX && p.K == 1) { s = p.pw_cols[f * 4 + 0]; q = p.pw_cols[f * 4 + 1]; }
     if (!isX && p.M == 1) { s = p.pw_cols[f * 4 + 2]; q = p.pw_cols[f * 4 + 3]; }
@@ -297,15 +308,16 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
 // The chain - one dependent DADD per row and column, 8 cycles on B200 - is the critical path, and the FP64 pipe
 // of one SM sub-partition issues a warp-wide DADD/DMUL only every ~2 cycles, so the sum chain (DMUL, DADD) and the
 // sum-of-squares chain (DMUL, DMUL, DADD) run in two different warps (two sub-partitions); each stays below the
-// 8-cycle chain latency.  Two producer warps gather 32 rows per stage with coalesced 16-byte cp.async (a warp-wide
+// 8-cycle chain latency (measured 14.6 cycles per row; a variant with extra "product" warps forming rn(rn(w z) z)
+// ahead of the chain was tried and was slower, 1.8 ms vs 1.5 ms at cfg 2).  Two producer warps gather 64 rows per stage with coalesced 16-byte cp.async (a warp-wide
 // instruction covers whole row segments; measured alternatives: per-row 256-byte TMA bulk copies are issue-bound,
 // 6.5 ms vs 2.3 ms at cfg 2, and a lane-per-row mapping is sector-request-bound, 7.4 ms) into an MOM_STAGES-deep
 // ring, each lane signalling the stage's mbarrier when its copies land (cp.async.mbarrier.arrive.noinc).  Row byte
 // offsets are computed once per stage and broadcast by shuffle; row indices are fetched a group of stages early.
 constexpr int MOM_COLS = 32;
 constexpr int MOM_ROWS = 64;                           // rows per stage: amortises the ~160 cycles of per-stage bookkeeping (ncu)
-constexpr int MOM_STAGES = 4;
-constexpr int MOM_THREADS = 128;                       // warp 0: sum chain, warp 1: sum-of-squares chain, warps 2-3: producers
+constexpr int MOM_STAGES = 4;                          // default ring depth (MomentParams::stages overrides it)
+constexpr int MOM_THREADS = 128;                       // warp 0: sum chain, warp 1: sum-of-squares chain, warps 2-3: loaders
 constexpr int MOM_GROUP = 4;                           // stages whose row indices are fetched together
 template <typename T> struct MomCfg { static constexpr int PITCH = MOM_COLS + 16 / sizeof(T); };  // 16-byte pad per row
 
@@ -314,10 +326,11 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int PITCH = MomCfg<T>::PITCH;
   T* sz = reinterpret_cast<T*>(smem_raw);                       // [STAGES][ROWS][PITCH]
-  T* swt = sz + (size_t)MOM_STAGES * MOM_ROWS * PITCH;           // [STAGES][ROWS]
-  T* sres = swt + MOM_STAGES * MOM_ROWS;                         // [COLS] sum-of-squares hand-over
+  const int NST = p.stages;
+  T* swt = sz + (size_t)NST * MOM_ROWS * PITCH;                  // [STAGES][ROWS]
+  T* sres = swt + NST * MOM_ROWS;                                // [COLS] sum-of-squares hand-over
   uint64_t* full = reinterpret_cast<uint64_t*>(sres + MOM_COLS);
-  uint64_t* empty = full + MOM_STAGES;
+  uint64_t* empty = full + NST;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f = blockIdx.y;
   const int64_t c0 = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * MOM_COLS;
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   const int64_t nst = (n + MOM_ROWS - 1) / MOM_ROWS;
 
   if (tid == 0) {
-    for (int s = 0; s < MOM_STAGES; ++s) { mbar_init(full + s, 64); mbar_init(empty + s, 2); }
+    for (int s = 0; s < NST; ++s) { mbar_init(full + s, 64); mbar_init(empty + s, 2); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -361,8 +374,8 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
       for (int j = 0; j < MOM_GROUP; ++j) {
         const int64_t st = st0 + j;
         if (st < nst) {
-          const int slot = (int)(st % MOM_STAGES);
-          const unsigned round = (unsigned)(st / MOM_STAGES);
+          const int slot = (int)(st % NST);
+          const unsigned round = (unsigned)(st / NST);
           if (round > 0) mbar_wait(empty + slot, (round & 1) ^ 1);
           const int64_t g = cur[j];
           const long long my_off = g >= 0 ? g * row_bytes : -1;   // byte offset of "my" row, -1: past the end
@@ -389,34 +402,36 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
     int slot = 0;
     unsigned parity = 0;
     int64_t left = n;
-    const T* zr = sz + lane;
-    const T* wr = swt;
-    for (int64_t st = 0; st < nst; ++st) {
-      mbar_wait(full + slot, parity);
-      if (left >= MOM_ROWS) {
-        if (warp == 0) {
+    {
+      const T* zr = sz + lane;
+      const T* wr = swt;
+      for (int64_t st = 0; st < nst; ++st) {
+        mbar_wait(full + slot, parity);
+        if (left >= MOM_ROWS) {
+          if (warp == 0) {
 #pragma unroll
-          for (int r = 0; r < MOM_ROWS; ++r) acc = Rn<T>::add(acc, Rn<T>::mul(zr[r * PITCH], wr[r]));
+            for (int r = 0; r < MOM_ROWS; ++r) acc = Rn<T>::add(acc, Rn<T>::mul(zr[r * PITCH], wr[r]));
+          } else {
+#pragma unroll
+            for (int r = 0; r < MOM_ROWS; ++r) {
+              const T z = zr[r * PITCH];
+              acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::mul(z, wr[r]), z));
+            }
+          }
         } else {
-#pragma unroll
-          for (int r = 0; r < MOM_ROWS; ++r) {
+          for (int r = 0; r < (int)left; ++r) {
             const T z = zr[r * PITCH];
-            acc = Rn<T>::add(acc, Rn<T>::mul(Rn<T>::mul(z, wr[r]), z));
+            const T wz = Rn<T>::mul(z, wr[r]);
+            acc = Rn<T>::add(acc, warp == 0 ? wz : Rn<T>::mul(wz, z));
           }
         }
-      } else {
-        for (int r = 0; r < (int)left; ++r) {
-          const T z = zr[r * PITCH];
-          const T wz = Rn<T>::mul(z, wr[r]);
-          acc = Rn<T>::add(acc, warp == 0 ? wz : Rn<T>::mul(wz, z));
-        }
+        left -= MOM_ROWS;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+        zr += MOM_ROWS * PITCH;
+        wr += MOM_ROWS;
+        if (++slot == NST) { slot = 0; parity ^= 1; zr = sz + lane; wr = swt; }
       }
-      left -= MOM_ROWS;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + slot);
-      zr += MOM_ROWS * PITCH;
-      wr += MOM_ROWS;
-      if (++slot == MOM_STAGES) { slot = 0; parity ^= 1; zr = sz + lane; wr = swt; }
     }
     if (warp == 1) sres[lane] = acc;
   }
@@ -425,9 +440,25 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
 }
 
 template <typename T>
-constexpr size_t moments_pipe_smem() {
-  return sizeof(T) * ((size_t)MOM_STAGES * MOM_ROWS * MomCfg<T>::PITCH + (size_t)MOM_STAGES * MOM_ROWS + MOM_COLS) +
-         2 * MOM_STAGES * sizeof(uint64_t);
+constexpr size_t moments_pipe_smem(int stages) {
+  return sizeof(T) * ((size_t)stages * MOM_ROWS * MomCfg<T>::PITCH + (size_t)stages * MOM_ROWS + MOM_COLS) +
+         2 * stages * sizeof(uint64_t);
+}
+constexpr int MOM_STAGES_DEEP = 8;      // few long chains: ~140 KB of gathered rows in flight per CTA
+
+// mean / std of every (fold, column) from the raw fold sums (deferred finalisation, see MomentParams::raw)
+template <typename T>
+__global__ void k_finalize_stats(MomentParams<T> p, int64_t nfolds) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t f = blockIdx.y;
+  if (c >= p.ld || f >= nfolds) return;
+  // column-sharded evaluation: only this shard's groups carry sums (p.stages = columns per group here); foreign
+  // entries stay zero so that the all-reduce across ranks assembles the rows
+  if (p.grp_stride > 1 && (int)((c / p.stages) % p.grp_stride) != p.grp0) return;
+  const T* r = p.raw + (size_t)f * 2 * p.ld;
+  MomentParams<T> q = p;
+  q.raw = nullptr;
+  finalize_column<T>(q, f, c, r[c], r[p.ld + c]);
 }
 
 }  // namespace cvmx

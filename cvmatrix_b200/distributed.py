@@ -39,6 +39,8 @@ class ShardedFolds:
         self.cvm, self.group, self.dist, self.torch = cvm, group, dist, torch
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # profiling aid: run this rank's share of a `shards`-way row-sharded step without any collective
+        self.emulate_shards = 0
         self.dev = torch.device("cuda", cvm.device)
         self.tdt = torch.float64 if np.dtype(cvm.dtype) == np.float64 else torch.float32
         self._gram: Optional["torch.Tensor"] = None
@@ -71,12 +73,13 @@ class ShardedFolds:
             return dict(out, fold_begin=o0, fold_end=o1)
         # ---- few large folds: rows of every fold split across ranks --------------------------------------
         sp, sc = C.c_void_p(), C.c_int64()
-        _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, self.world, C.byref(sp), C.byref(sc)), h)
+        shards = self.emulate_shards or self.world
+        _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, shards, C.byref(sp), C.byref(sc)), h)
         n = lib.cvmx_sharded_gram_count(h, f0, f1, 3)
         if self._gram is None or self._gram.numel() < n:
             self._gram = t.empty((n,), dtype=t.float64, device=self.dev)
         gram = self._gram[:n]
-        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, self.world, vp(gram)), h)
+        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, shards, vp(gram)), h)
         _lib.check(lib.cvmx_sharded_stats_wait(h), h)   # the chains ran on a side stream beside the Gram kernel
         if self.world > 1:
             stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8" if self.tdt == t.float64 else "<f4"), device=self.dev)
