@@ -53,6 +53,8 @@ struct cvmx_handle {
   // side stream for the statistics kernels when they can overlap the Gram kernel (large, row-split folds and fit)
   cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mass = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_stage[2] = {nullptr, nullptr};   // fit: staged host->device upload
+  DevBuf stage[2];
   // fitted state
   bool fitted = false, weighted = false;
   int64_t N = 0, K = 0, M = 0, ld = 0;
@@ -404,7 +406,30 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   T* Z = h->Z.as<T>();
   if (N > 0) {
     if (ld > K + M) CU(h, cudaMemset2DAsync(Z + (K + M), ld * sz, 0, (ld - K - M) * sz, N, h->stream));
-    CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
+    if (mem == CVMX_HOST && ldx == K && (size_t)N * K * sz >= ((size_t)64 << 20)) {
+      // Large host matrix: a pitch-changing 2-D copy makes the DMA engine move 4000-byte rows one by one (~20 GB/s
+      // from pinned memory, measured); instead stream contiguous chunks into two staging buffers on a copy stream
+      // (full PCIe rate) and re-pitch them into Z with a kernel on the main stream, double-buffered.
+      const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(((size_t)128 << 20) / ((size_t)K * sz)));
+      CU(h, h->stage[0].reserve((size_t)chunk_rows * K * sz));
+      CU(h, h->stage[1].reserve((size_t)chunk_rows * K * sz));
+      int c = 0;
+      for (int64_t r0 = 0; r0 < N; r0 += chunk_rows, ++c) {
+        const int64_t nr = std::min(chunk_rows, N - r0);
+        const int b = c & 1;
+        if (c >= 2) CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[b], 0));       // staging buffer free again
+        else if (c == 0) { CU(h, cudaEventRecord(h->ev_fork, h->stream)); CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_fork, 0)); }
+        CU(h, cudaMemcpyAsync(h->stage[b].p, (const char*)X + (size_t)r0 * K * sz, (size_t)nr * K * sz, cudaMemcpyHostToDevice, h->aux2_stream));
+        CU(h, cudaEventRecord(h->ev_copied[b], h->aux2_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
+        k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>(h->stage[b].as<T>(), nr, K, Z + r0 * ld, ld);
+        h->launches++;
+        CU(h, cudaEventRecord(h->ev_stage[b], h->stream));
+      }
+      CU(h, cudaGetLastError());
+    } else {
+      CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
+    }
     if (M > 0) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
     if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
     else { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
@@ -764,6 +789,10 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   if ((e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaStreamCreateWithPriority(&h->aux2_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_mass, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_copied[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_copied[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
     delete h;
@@ -785,6 +814,11 @@ int32_t cvmx_destroy(cvmx_t* h) {
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
   if (h->aux2_stream) { cudaStreamSynchronize(h->aux2_stream); cudaStreamDestroy(h->aux2_stream); }
   if (h->ev_mass) cudaEventDestroy(h->ev_mass);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
+    h->stage[i].release();
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -436,6 +436,16 @@ __global__ void k_normalize_indices(int64_t* __restrict__ idx, int64_t n, int64_
   idx[i] = v;
 }
 
+// Dense staged rows (rows x cols, contiguous) -> columns [col0, col0 + cols) of the padded device matrix.
+template <typename T>
+__global__ void k_repack(const T* __restrict__ src, int64_t rows, int64_t cols, T* __restrict__ dst, int64_t ld) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    dst[r * ld + c] = src[e];
+  }
+}
+
 template <typename T>
 __global__ void k_fill(T* __restrict__ p, int64_t n, T v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

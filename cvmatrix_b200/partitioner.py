@@ -90,18 +90,41 @@ class Partitioner:
         n = arr.shape[0]
         if n == 0:
             return [], np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
-        _, first, inverse = np.unique(arr, return_index=True, return_inverse=True)
-        inverse = inverse.reshape(-1)
-        order = np.argsort(first, kind="stable")          # unique values by first appearance
-        rank = np.empty_like(order)
-        rank[order] = np.arange(order.size)
-        group = rank[inverse]                              # fold position of every row
-        counts = np.bincount(group, minlength=order.size)
-        offsets = np.zeros(order.size + 1, dtype=np.int64)
+        group = first = None
+        if arr.dtype.kind in "iub":
+            # integer labels in a small range: counting pass instead of a comparison sort
+            lo, hi = int(arr.min()), int(arr.max())
+            span = hi - lo + 1
+            if span <= max(4 * n, 1 << 16) and span <= (1 << 26):
+                rel = (arr.astype(np.int64, copy=False) - lo) if arr.dtype.kind != "b" else arr.astype(np.int64)
+                first_of = np.full(span, n, dtype=np.int64)
+                first_of[rel[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)   # last write wins = first occurrence
+                present = np.flatnonzero(first_of < n)
+                order = present[np.argsort(first_of[present], kind="stable")]    # label values by first appearance
+                rank = np.empty(span, dtype=np.int64)
+                rank[order] = np.arange(order.size)
+                group = rank[rel]
+                first = first_of[order]
+                n_groups = order.size
+        if group is None:
+            _, first_u, inverse = np.unique(arr, return_index=True, return_inverse=True)
+            inverse = inverse.reshape(-1)
+            order = np.argsort(first_u, kind="stable")         # unique values by first appearance
+            rank = np.empty_like(order)
+            rank[order] = np.arange(order.size)
+            group = rank[inverse]                              # fold position of every row
+            first = first_u[order]
+            n_groups = order.size
+        counts = np.bincount(group, minlength=n_groups)
+        offsets = np.zeros(n_groups + 1, dtype=np.int64)
         np.cumsum(counts, out=offsets[1:])
-        small = np.int32 if order.size < 2**31 else np.int64
-        indices = np.argsort(group.astype(small, copy=False), kind="stable").astype(np.int64, copy=False)
-        keys = [arr[i] for i in first[order]]              # numpy scalars, like iterating the array
+        if n_groups == n:
+            indices = first.astype(np.int64, copy=True)        # every label unique (leave-one-out): no sort needed
+        else:
+            # numpy's stable sort is a radix sort for 16-bit keys
+            small = np.uint16 if n_groups <= (1 << 16) else (np.int32 if n_groups < 2**31 else np.int64)
+            indices = np.argsort(group.astype(small, copy=False), kind="stable").astype(np.int64, copy=False)
+        keys = [arr[i] for i in first]                         # numpy scalars, like iterating the array
         return keys, offsets, np.ascontiguousarray(indices)
 
     @staticmethod

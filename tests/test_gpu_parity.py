@@ -352,3 +352,33 @@ def test_sharded_phases_match_unsharded(n_shards):
         assert np.array_equal(ost[pos, 0, :K].cpu().numpy(), ref["X_mean"][f][0])
         assert np.array_equal(ost[pos, 1, K:].cpu().numpy(), ref["Y_std"][f][0])
         assert osc[pos, 0].item() == ref["sum_w_train"][f] and oss[pos].item() == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_wide_k_and_m_multi_tile(dtype):
+    """cfg 5 in miniature: K spans 6 column blocks, the Y columns straddle two blocks (K = 700, M = 150), 10 folds;
+    un-centred so that float32 is comparable to numpy-float32 at 1e-5."""
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    X, Y, w, folds = make_inputs(6000, 700, 150, 10, dtype=dtype, seed=3)
+    flags = (False, False, False, False) if dtype == np.float32 else (True, True, True, True)
+    orc = OracleCVMatrix(*flags, dtype=dtype)
+    orc.fit(X, Y, w)
+    m = CVMatrix(*flags, dtype=dtype)
+    m.fit(X, Y, w)
+    tol = TOL[np.dtype(dtype).name]
+    assert rel_fro(m.XTX, orc.XTX) <= tol and rel_fro(m.XTY, orc.XTY) <= tol
+    part = Partitioner(folds)
+    m.set_folds(part)
+    out = m.training_batch()
+    for pos in (0, 4, 9):
+        r = orc.fold(part.get_validation_indices(pos))
+        assert out["XTX"][pos].dtype == dtype
+        assert rel_fro(out["XTX"][pos], r.XTX) <= tol and rel_fro(out["XTY"][pos], r.XTY) <= tol
+        assert np.array_equal(out["XTX"][pos], out["XTX"][pos].T)
+        if dtype == np.float64:
+            assert np.array_equal(out["X_std"][pos], r.X_std) and np.array_equal(out["Y_mean"][pos], r.Y_mean)
+    # XTY only / XTX only take the reduced tile sets
+    xty, _ = m.training_XTY(part.get_validation_indices(3))
+    xtx, _ = m.training_XTX(part.get_validation_indices(3))
+    assert rel_fro(xty, out["XTY"][3]) <= 1e-13 and rel_fro(xtx, out["XTX"][3]) <= 1e-13
