@@ -1020,6 +1020,28 @@ int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count) {
   return CVMX_OK;
 }
 
+// Host-side CSR builder for integer fold labels (no device work): labels in [lo, lo + span) -> fold order by first
+// appearance, offsets and ascending row indices, in two O(N) counting passes.  scratch: 2 * span int64.
+int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch,
+                              int64_t* first_rows /* span */, int64_t* offsets /* span + 1 */, int64_t* indices /* n */) {
+  if (!labels || n < 0 || span <= 0 || !scratch || !first_rows || !offsets || !indices) return -1;
+  int64_t* slot = scratch;          // label -> fold position (-1: unseen)
+  int64_t* count = scratch + span;  // per fold position
+  for (int64_t l = 0; l < span; ++l) { slot[l] = -1; count[l] = 0; }
+  int64_t n_folds = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t l = labels[i] - lo;
+    if (l < 0 || l >= span) return -1;
+    int64_t s = slot[l];
+    if (s < 0) { s = slot[l] = n_folds; first_rows[n_folds++] = i; }
+    count[s]++;
+  }
+  offsets[0] = 0;
+  for (int64_t s = 0; s < n_folds; ++s) { offsets[s + 1] = offsets[s] + count[s]; count[s] = offsets[s]; }
+  for (int64_t i = 0; i < n; ++i) indices[count[slot[labels[i] - lo]]++] = i;
+  return n_folds;
+}
+
 int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }
 int64_t cvmx_ld(const cvmx_t* h) { return h ? h->ld : 0; }
 

@@ -96,6 +96,9 @@ class Partitioner:
             lo, hi = int(arr.min()), int(arr.max())
             span = hi - lo + 1
             if span <= max(4 * n, 1 << 16) and span <= (1 << 26):
+                native = Partitioner._partition_native(arr, lo, span) if (4 * span <= n or span <= (1 << 16)) else None
+                if native is not None:
+                    return native
                 rel = (arr.astype(np.int64, copy=False) - lo) if arr.dtype.kind != "b" else arr.astype(np.int64)
                 first_of = np.full(span, n, dtype=np.int64)
                 first_of[rel[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)   # last write wins = first occurrence
@@ -126,6 +129,31 @@ class Partitioner:
             indices = np.argsort(group.astype(small, copy=False), kind="stable").astype(np.int64, copy=False)
         keys = [arr[i] for i in first]                         # numpy scalars, like iterating the array
         return keys, offsets, np.ascontiguousarray(indices)
+
+    @staticmethod
+    def _partition_native(arr: np.ndarray, lo: int, span: int):
+        """Two counting passes in the C library (host code of libcvmx.so); None if the library is not built."""
+        try:
+            from . import _lib
+
+            lib = _lib.load()
+        except (ImportError, OSError):
+            return None
+        import ctypes as C
+
+        n = arr.shape[0]
+        labels = np.ascontiguousarray(arr, dtype=np.int64)
+        scratch = np.empty(2 * span, dtype=np.int64)
+        first = np.empty(min(span, n), dtype=np.int64)
+        offsets = np.empty(min(span, n) + 1, dtype=np.int64)
+        indices = np.empty(n, dtype=np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        nf = lib.cvmx_partition_labels(p(labels), n, lo, span, p(scratch), p(first), p(offsets), p(indices))
+        if nf < 0:
+            return None
+        first = first[:nf]
+        keys = [arr[i] for i in first]   # numpy scalars, like iterating the array
+        return keys, offsets[: nf + 1].copy(), indices
 
     @staticmethod
     def _partition_hashable(folds: Iterable[Hashable]):

@@ -165,6 +165,13 @@ int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1,
 int32_t cvmx_profile_enable(cvmx_t* h, int32_t on);
 int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count);
 
+/* Host-only helper (no CUDA call): CSR of validation sets from integer fold labels, replacing the Python loop of
+ * Partitioner._init_folds_dict (cvmatrix/partitioner.py:101-107).  labels[i] in [lo, lo + span); folds are ordered
+ * by first appearance; first_rows[k] = first row of fold k, offsets / indices = CSR (indices ascending per fold).
+ * scratch needs 2 * span int64.  Returns the number of folds, or -1 on bad arguments. */
+int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch,
+                              int64_t* first_rows, int64_t* offsets, int64_t* indices);
+
 /* Introspection used by tests / bench: number of kernels launched by this handle so far, and
  * the padded leading dimension of the device matrices. */
 int64_t cvmx_launch_count(const cvmx_t* h);
