@@ -336,17 +336,28 @@ def main():
         e2e_steps = args.steps if cfg["P"] <= 1000 else max(1, min(args.steps, 2))
         out_bytes = 0
 
+        parts = {"partitioner_ms": 0.0, "fit_ms": 0.0, "set_folds_ms": 0.0, "folds_ms": 0.0}
+
         def e2e_step():
             nonlocal out_bytes
+            t0 = time.perf_counter()
             p2 = Partitioner(folds)
+            t1 = time.perf_counter()
             m.fit(X, Y, w)
+            t2 = time.perf_counter()
             m.set_folds(p2)
+            t3 = time.perf_counter()
             out_bytes = 0
             for c0 in range(f0, f1, chunk):
                 r = m.training_batch(c0, min(f1, c0 + chunk), out="numpy")
                 out_bytes += r["XTX"].nbytes + r["XTY"].nbytes + 2 * r["X_mean"].nbytes + 2 * r["Y_mean"].nbytes
+            t4 = time.perf_counter()
+            for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                parts[k] += v * 1e3
 
         e2e_step()
+        for k in parts:
+            parts[k] = 0.0
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -360,7 +371,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": P / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + w.nbytes + part.indices.nbytes + part.offsets.nbytes),
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "includes": "Partitioner + fit (H2D from pinned host memory) + set_folds + all folds + D2H of every output"}
+               "includes": "Partitioner + fit (H2D from pinned host memory) + set_folds + all folds + D2H of every output",
+               "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
 
     # ---- CPU baseline: numpy restatement of the reference on this box's host cores (rank 0, N = 1 only) ----
     cpu = None

@@ -404,32 +404,14 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   CU(h, h->fit_scal.reserve(sizeof(FitScalars)));
   const cudaMemcpyKind kind = mem == CVMX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   T* Z = h->Z.as<T>();
+  // Large host matrix: a pitch-changing 2-D copy makes the DMA engine move 4000-byte rows one by one (~20 GB/s from
+  // pinned memory, measured).  Instead stream contiguous chunks into two staging buffers on a copy stream (full PCIe
+  // rate), re-pitch each into Z with a kernel, and run the chunk's share of the Gram pass and of the moment chains
+  // right behind it, so that fit costs little more than the host->device copy.
+  const bool chunked = N > 0 && mem == CVMX_HOST && ldx == K && K > 1 && (size_t)N * K * sz >= ((size_t)64 << 20);
   if (N > 0) {
     if (ld > K + M) CU(h, cudaMemset2DAsync(Z + (K + M), ld * sz, 0, (ld - K - M) * sz, N, h->stream));
-    if (mem == CVMX_HOST && ldx == K && (size_t)N * K * sz >= ((size_t)64 << 20)) {
-      // Large host matrix: a pitch-changing 2-D copy makes the DMA engine move 4000-byte rows one by one (~20 GB/s
-      // from pinned memory, measured); instead stream contiguous chunks into two staging buffers on a copy stream
-      // (full PCIe rate) and re-pitch them into Z with a kernel on the main stream, double-buffered.
-      const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(((size_t)128 << 20) / ((size_t)K * sz)));
-      CU(h, h->stage[0].reserve((size_t)chunk_rows * K * sz));
-      CU(h, h->stage[1].reserve((size_t)chunk_rows * K * sz));
-      int c = 0;
-      for (int64_t r0 = 0; r0 < N; r0 += chunk_rows, ++c) {
-        const int64_t nr = std::min(chunk_rows, N - r0);
-        const int b = c & 1;
-        if (c >= 2) CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[b], 0));       // staging buffer free again
-        else if (c == 0) { CU(h, cudaEventRecord(h->ev_fork, h->stream)); CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_fork, 0)); }
-        CU(h, cudaMemcpyAsync(h->stage[b].p, (const char*)X + (size_t)r0 * K * sz, (size_t)nr * K * sz, cudaMemcpyHostToDevice, h->aux2_stream));
-        CU(h, cudaEventRecord(h->ev_copied[b], h->aux2_stream));
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
-        k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>(h->stage[b].as<T>(), nr, K, Z + r0 * ld, ld);
-        h->launches++;
-        CU(h, cudaEventRecord(h->ev_stage[b], h->stream));
-      }
-      CU(h, cudaGetLastError());
-    } else {
-      CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
-    }
+    if (!chunked) CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
     if (M > 0) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
     if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
     else { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
@@ -437,16 +419,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   CU(h, cudaMemsetAsync(h->Ttot.p, 0, (size_t)K * ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->sum_z.p, 0, ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->sumsq_z.p, 0, ld * sz, h->stream));
-
   CU(h, h->pwcols.reserve(4 * sz));
-  // moment chains (4-5 ms at N = 1M: 8 cycles per row and column, unsplittable) run beside the Gram kernel
-  cudaStream_t main_stream;
-  int32_t rc0 = fork_stats(h, &main_stream);
-  if (rc0) return rc0;
-  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
-                                                   h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
-  h->launches++;
-  CU(h, cudaGetLastError());
 
   MomentParams<T> mp;
   mp.Z = Z; mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
@@ -454,25 +427,121 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   mp.flags = h->flags; mp.resolution = (T)h->resolution;
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
-  int32_t rc = launch_moments<T>(h, mp, 1, N);
-  if (rc) { h->stream = main_stream; return rc; }
-  rc = join_stats(h, main_stream);
-  if (rc) return rc;
 
-  // totals: Gram over the row slab [g0, g1) with identity indexing, raw epilogue into Ttot
   Plan pl;
   plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), pl.tiles);
-  const int64_t off[2] = {g0, g1};
-  plan_units(h, off, 0, 1, (int)pl.tiles.size(), pl);
   EpiParams<T> epi;
   epi.mode = 0; epi.flags = 0; epi.want = CVMX_WANT_XTX | CVMX_WANT_XTY;
   epi.K = K; epi.M = M; epi.ld = ld;
   epi.Ttot = nullptr; epi.stats = nullptr; epi.fs = nullptr;
   epi.out_xx = h->Ttot.as<T>(); epi.xx_pitch = ld; epi.xx_stride = 0;
   epi.out_xy = h->Ttot.as<T>() + K; epi.xy_pitch = ld; epi.xy_stride = 0;
-  if (g1 > g0) {
-    rc = launch_gram<T>(h, pl, nullptr, epi);
+
+  // statistics run on the side stream (moment chains: ~15 cycles per row and column, unsplittable by rows)
+  cudaStream_t main_stream;
+  int32_t rc0 = fork_stats(h, &main_stream);
+  if (rc0) return rc0;
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(Z, h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
+                                                   h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
+  h->launches++;
+  int32_t rc = CVMX_OK;
+  if (!chunked) {
+    rc = launch_moments<T>(h, mp, 1, N);
+    if (rc) { h->stream = main_stream; return rc; }
+    rc = join_stats(h, main_stream);
     if (rc) return rc;
+    // totals: Gram over the row slab [g0, g1) with identity indexing, raw epilogue into Ttot
+    const int64_t off[2] = {g0, g1};
+    plan_units(h, off, 0, 1, (int)pl.tiles.size(), pl);
+    if (g1 > g0) {
+      rc = launch_gram<T>(h, pl, nullptr, epi);
+      if (rc) return rc;
+    }
+  } else {
+    cudaStream_t stats_stream = h->stream;   // side stream (fork_stats made it current)
+    h->stream = main_stream;
+    const int ntiles = (int)pl.tiles.size();
+    const int64_t chunk_rows = std::max<int64_t>(GBK, (int64_t)(((size_t)128 << 20) / ((size_t)K * sz)) / GBK * GBK);
+    const int64_t unit_rows = 2816;          // ~176 stages per Gram CTA
+    // units of every chunk (clipped to the Gram slab [g0, g1)), numbered globally: one fold with `total` splits
+    std::vector<int64_t> chunk_unit0;
+    for (int64_t r0 = 0; r0 < N; r0 += chunk_rows) {
+      chunk_unit0.push_back((int64_t)pl.units.size());
+      const int64_t a0 = std::max(r0, g0), a1 = std::min(std::min(r0 + chunk_rows, N), g1);
+      for (int64_t u0 = a0; u0 < a1; u0 += unit_rows) {
+        GramUnit u;
+        u.row_begin = u0; u.row_end = std::min(a1, u0 + unit_rows);
+        u.fold = 0; u.split = (int32_t)pl.units.size(); u.nsplit = 0; u.part_base = 0;
+        pl.units.push_back(u);
+      }
+    }
+    chunk_unit0.push_back((int64_t)pl.units.size());
+    const int32_t total = (int32_t)pl.units.size();
+    for (auto& u : pl.units) u.nsplit = total;                // force_partials: always the partial + reduce path
+    pl.fold_units.assign(1, 0);
+    pl.split_folds.assign(1, 0);
+    GramParams<T> gp;
+    gp.Z = Z; gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
+    gp.ntiles = ntiles; gp.raw_out = nullptr; gp.force_partials = 1; gp.epi = epi;
+    const size_t smem = gram_smem_bytes<T>();
+    if (total > 0) {
+      CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
+      CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
+      CU(h, h->fold_units.reserve(sizeof(int32_t)));
+      CU(h, h->split_folds.reserve(sizeof(int32_t)));
+      CU(h, h->partials.reserve((size_t)total * ntiles * GACC * GTHREADS * sizeof(double)));
+      CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaMemsetAsync(h->fold_units.p, 0, sizeof(int32_t), h->stream));
+      CU(h, cudaMemsetAsync(h->split_folds.p, 0, sizeof(int32_t), h->stream));
+      if (!h->attr_gram) {
+        CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(h, cudaFuncSetAttribute(k_gram_reduce<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->attr_gram = true;
+      }
+    }
+    gp.tiles = h->tiles.as<int2>(); gp.partials = h->partials.as<double>();
+    CU(h, h->stage[0].reserve((size_t)chunk_rows * K * sz));
+    CU(h, h->stage[1].reserve((size_t)chunk_rows * K * sz));
+    CU(h, cudaEventRecord(h->ev_mass, h->stream));                    // Y, w, pad and the unit table are queued
+    CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+    int c = 0;
+    for (int64_t r0 = 0; r0 < N; r0 += chunk_rows, ++c) {
+      const int64_t nr = std::min(chunk_rows, N - r0);
+      const int b = c & 1;
+      if (c >= 2) CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[b], 0));       // staging buffer free again
+      CU(h, cudaMemcpyAsync(h->stage[b].p, (const char*)X + (size_t)r0 * K * sz, (size_t)nr * K * sz, cudaMemcpyHostToDevice, h->aux2_stream));
+      CU(h, cudaEventRecord(h->ev_copied[b], h->aux2_stream));
+      CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
+      k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>(h->stage[b].as<T>(), nr, K, Z + r0 * ld, ld);
+      h->launches++;
+      CU(h, cudaEventRecord(h->ev_stage[b], h->stream));
+      // the chunk's rows of the moment chains, continuing the accumulators of the previous chunk
+      CU(h, cudaStreamWaitEvent(stats_stream, h->ev_stage[b], 0));
+      MomentParams<T> mc = mp;
+      mc.row0 = r0; mc.N = nr; mc.accumulate = c > 0;
+      h->stream = stats_stream;
+      rc = launch_moments<T>(h, mc, 1, nr);
+      h->stream = main_stream;
+      if (rc) return rc;
+      // the chunk's Gram partials
+      const int64_t nu = chunk_unit0[c + 1] - chunk_unit0[c];
+      if (nu > 0) {
+        gp.units = h->units.as<GramUnit>() + chunk_unit0[c];
+        const int ev0 = prof_mark(h);
+        k_gram<T><<<(unsigned)(nu * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+        h->launches++;
+        prof_span(h, PROF_GRAM, ev0, prof_mark(h));
+      }
+    }
+    CU(h, cudaGetLastError());
+    if (total > 0) {
+      gp.units = h->units.as<GramUnit>();
+      k_gram_reduce<T><<<dim3(ntiles, 1), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+      h->launches++;
+      CU(h, cudaGetLastError());
+    }
+    CU(h, cudaEventRecord(h->ev_join, stats_stream));
   }
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   FitScalars fsc;

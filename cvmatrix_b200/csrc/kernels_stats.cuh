@@ -224,6 +224,8 @@ struct MomentParams {
   T* raw = nullptr;             // [P][2][ld]: if set, store the raw fold sums (s, q) here and leave mean / std to
                                 // k_finalize_stats - the chains then do not depend on the weight-mass kernel
   int stages = 4;               // ring depth of k_moments_pipe (runtime: few long chains want more bytes in flight)
+  int64_t row0 = 0;             // fit mode: rows [row0, row0 + N) ...
+  int accumulate = 0;           // ... continuing the chains stored in sum_z / sumsq_z (chunk-pipelined fit)
 };
 
 template <typename T>
@@ -280,11 +282,12 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
   const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
   T s = T(0), q = T(0);
+  if (p.accumulate) { s = p.sum_z[c]; q = p.sumsq_z[c]; }
   int64_t i = 0;
   for (; i + 4 <= n; i += 4) {
     int64_t r[4]; T z[4], wv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) r[j] = idx ? idx[i + j] : i + j;
+    for (int j = 0; j < 4; ++j) r[j] = idx ? idx[i + j] : p.row0 + i + j;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { z[j] = p.Z[r[j] * p.ld + c]; wv[j] = p.w[r[j]]; }
 #pragma unroll
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
     }
   }
   for (; i < n; ++i) {
-    const int64_t r = idx ? idx[i] : i;
+    const int64_t r = idx ? idx[i] : p.row0 + i;
     const T z = p.Z[r * p.ld + c];
     const T wz = Rn<T>::mul(z, p.w[r]);
     s = Rn<T>::add(s, wz);
@@ -346,6 +349,7 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   __syncthreads();
 
   T acc = T(0);
+  if (p.accumulate && warp < 2) acc = warp == 0 ? p.sum_z[c0 + lane] : p.sumsq_z[c0 + lane];
   if (warp >= 2) {
     // ---------------- producers: warp 2 + pw owns rows [16 pw, 16 pw + 16) of every stage ----------------
     // A warp-wide cp.async covers RPI whole row segments (coalesced 16-byte chunks); the byte offset of each row is
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
 #pragma unroll
       for (int j = 0; j < MOM_GROUP; ++j) {
         const int64_t row = (st0 + j) * MOM_ROWS + pw * PROWS + (lane % PROWS);
-        g[j] = row < n ? (idx ? idx[row] : row) : -1;
+        g[j] = row < n ? (idx ? idx[row] : p.row0 + row) : -1;
       }
     };
     fetch(0, cur);
