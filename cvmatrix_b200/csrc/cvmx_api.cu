@@ -137,7 +137,13 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
   int64_t rows_per_unit = INT64_MAX;
   if (Pn * ntiles < 8 * sms) {
     double best = -1;
-    for (int64_t R = 2048; R <= 4096; R += GBK) {
+    // wide K: the tiles alone fill the GPU, and every split costs ntiles x 128 KB of partial workspace - keep the
+    // workspace below ~2 GB by making the units longer
+    int64_t total_rows = 0;
+    for (int64_t f = f0; f < f1; ++f) total_rows += off[f + 1] - off[f];
+    const int64_t max_units = std::max<int64_t>(Pn, (int64_t)(((size_t)2 << 30) / ((size_t)std::max(ntiles, 1) * GACC * GTHREADS * sizeof(double))));
+    const int64_t r_min = std::max<int64_t>(2048, round_up((total_rows + max_units - 1) / max_units, GBK));
+    for (int64_t R = r_min; R <= r_min + 2048; R += GBK) {
       int64_t items = 0;
       for (int64_t f = f0; f < f1; ++f) items += std::max<int64_t>(1, (off[f + 1] - off[f] + R - 1) / R);
       items *= ntiles;
@@ -476,6 +482,10 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       }
     }
     chunk_unit0.push_back((int64_t)pl.units.size());
+    // wide K: one partial per 2816 rows x ntiles tiles would not fit (K = 5000: 107 MB per unit) - then the Gram pass
+    // runs after the upload with longer units instead of chunk by chunk
+    const bool pipeline_gram = (size_t)pl.units.size() * ntiles * GACC * GTHREADS * sizeof(double) <= ((size_t)2 << 30);
+    if (!pipeline_gram) { pl.units.clear(); for (auto& u0 : chunk_unit0) u0 = 0; }
     const int32_t total = (int32_t)pl.units.size();
     for (auto& u : pl.units) u.nsplit = total;                // force_partials: always the partial + reduce path
     pl.fold_units.assign(1, 0);
@@ -542,6 +552,14 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       CU(h, cudaGetLastError());
     }
     CU(h, cudaEventRecord(h->ev_join, stats_stream));
+    if (!pipeline_gram && g1 > g0) {
+      Plan pg;
+      pg.tiles = pl.tiles;
+      const int64_t off[2] = {g0, g1};
+      plan_units(h, off, 0, 1, ntiles, pg);
+      rc = launch_gram<T>(h, pg, nullptr, epi);
+      if (rc) return rc;
+    }
   }
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   FitScalars fsc;

@@ -117,6 +117,29 @@ class CVMatrix:
         _lib.check(rc, None)
         self._partitioner: Optional[Partitioner] = None
 
+    # ---- pickling (the reference object is a plain picklable container that callers ship to worker processes,
+    # cvmatrix/partitioner.py:26-31): device state is dropped and rebuilt from the host arrays on load -----------
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items() if k not in ("_lib", "_h", "_partitioner")}
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._lib = _lib.load()
+        self._partitioner = None
+        self._h = C.c_void_p()
+        rc = self._lib.cvmx_create(
+            self.device, _lib.F64 if np.dtype(self.dtype) == np.float64 else _lib.F32, self._flags, int(self.ddof),
+            float(self.resolution), C.byref(self._h),
+        )
+        _lib.check(rc, None)
+        if self.X is not None:
+            keep, self.copy = self.copy, False   # the unpickled arrays are already private copies
+            try:
+                self.fit(self.X, self.Y, None if self.weights is None else self.weights)
+            finally:
+                self.copy = keep
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -382,3 +382,31 @@ def test_wide_k_and_m_multi_tile(dtype):
     xty, _ = m.training_XTY(part.get_validation_indices(3))
     xtx, _ = m.training_XTX(part.get_validation_indices(3))
     assert rel_fro(xty, out["XTY"][3]) <= 1e-13 and rel_fro(xtx, out["XTX"][3]) <= 1e-13
+
+
+def test_pickle_roundtrip_and_abi_misuse():
+    import ctypes as C
+    import pickle
+
+    from cvmatrix_b200 import CVMatrix, _lib
+
+    X, Y, w, folds = make_inputs(2000, 30, 3, 4, seed=21)
+    m = CVMatrix()
+    val = np.flatnonzero(folds == 2)
+    # calls before fit are rejected, as is a fold range outside the CSR
+    with pytest.raises(ValueError):
+        m.training_XTX(val)
+    m.fit(X, Y, w)
+    with pytest.raises(ValueError):
+        m._lib.cvmx_training_batch  # noqa: B018 - attribute exists
+        _lib.check(m._lib.cvmx_training_batch(m._h, 0, 3, 3, None, None, None, None, None, _lib.HOST), m._h)
+    ref = m.training_XTX_XTY(val)
+    m2 = pickle.loads(pickle.dumps(m))
+    got = m2.training_XTX_XTY(val)
+    assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[0][1], ref[0][1])
+    for a, b in zip(got[1], ref[1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(m2.XTX, m.XTX) and m2.sum_w == m.sum_w
+    h = C.c_void_p()
+    assert m._lib.cvmx_create(0, 7, 15, 1, 1e-14, C.byref(h)) == _lib.ERR_INVALID   # bad dtype code
+    assert m._lib.cvmx_create(99, _lib.F64, 15, 1, 1e-14, C.byref(h)) == _lib.ERR_INVALID   # no such device
