@@ -410,3 +410,24 @@ def test_pickle_roundtrip_and_abi_misuse():
     h = C.c_void_p()
     assert m._lib.cvmx_create(0, 7, 15, 1, 1e-14, C.byref(h)) == _lib.ERR_INVALID   # bad dtype code
     assert m._lib.cvmx_create(99, _lib.F64, 15, 1, 1e-14, C.byref(h)) == _lib.ERR_INVALID   # no such device
+
+
+def test_many_folds_exceed_one_grid_dimension():
+    """70 000 leave-one-out folds (> 65 535, the y-dimension limit of a launch): the statistics and streaming kernels
+    are issued in fold chunks; spot-check folds on both sides of every chunk boundary."""
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    N, K, M = 70_000, 12, 2
+    X, Y, w, _ = make_inputs(N, K, M, 1, seed=8)
+    orc = OracleCVMatrix()
+    orc.fit(X, Y, w)
+    m = CVMatrix()
+    m.fit(X, Y, w)
+    m.set_folds(Partitioner(np.arange(N)))
+    out = m.training_batch()
+    assert out["XTX"].shape == (N, K, K)
+    for f in (0, 65_534, 65_535, 65_536, 69_999):
+        r = orc.fold(np.array([f]))
+        assert rel_fro(out["XTX"][f], r.XTX) <= 1e-12 and rel_fro(out["XTY"][f], r.XTY) <= 1e-12
+        assert np.array_equal(out["X_mean"][f], r.X_mean) and np.array_equal(out["Y_std"][f], r.Y_std)
+    assert int(out["status"].max()) == 0
