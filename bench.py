@@ -40,6 +40,8 @@ CONFIGS = {
     "cfg2": dict(N=1_000_000, K=500, M=10, P=5, name="N=1M K=500 M=10 f64 weighted center+scale 5-fold"),
     "cfg3": dict(N=1_000_000, K=500, M=10, P=1000, name="N=1M K=500 M=10 f64 weighted center+scale 1000-fold"),
     "cfg4": dict(N=20_000, K=500, M=10, P=20_000, name="LOO N=20k K=500 M=10 f64 weighted center+scale"),
+    # contract self-test shape (tests/test_bench_contract.py)
+    "tiny": dict(N=4_000, K=24, M=3, P=4, name="self-test: N=4k K=24 M=3 f64 4-fold"),
     # cfg 5 (wide, K=5000 M=100) at reduced N: the full N=2M matrix is 80 GB and cannot be generated on the host
     "cfg5s": dict(N=100_000, K=5000, M=100, P=10, name="wide K=5000 M=100 f64 weighted center+scale 10-fold at N=100k (cfg 5 scaled to 1/20 of its rows)"),
     # reduced shapes for ncu captures only (same per-CTA work as cfg2 / cfg3 / cfg4, fewer CTAs)
