@@ -303,15 +303,26 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
 
+  // Diagonal tiles only need their upper triangle: the warp tiles (rows 64-127) x (cols 0-63) of warps 4 and 5 are
+  // never used.  Those two warps instead help warps 6 and 7 - which sit on the other two sub-partitions - by taking
+  // every other pipeline stage of their tiles (intra-CTA split-K), so each sub-partition carries 1.5 instead of 2
+  // warp-tiles of DMMA work; the two partial accumulators are added through shared memory before the epilogue.
+  const bool half = diag && wm == 1;                 // this warp computes every other stage
+  const bool helper = half && wn < 2;                // ... of the tile of warp (1, wn + 2)
+  const int ewn = helper ? wn + 2 : wn;
+  const int my_parity = helper ? 1 : 0;
+
 #pragma unroll 1
   for (int64_t kt = 0; kt < nk; ++kt) {
     const int slot = (int)(kt % GSTAGES);
     mbar_wait(full + slot, (unsigned)(kt / GSTAGES) & 1);
     const T* a_base = sA + (size_t)slot * GBK * PITCH + wm * 64 + 2 * g;
-    const T* b_base = (diag ? sA : sB) + (size_t)slot * GBK * PITCH + wn * 32 + 2 * g;
+    const T* b_base = (diag ? sA : sB) + (size_t)slot * GBK * PITCH + ewn * 32 + 2 * g;
     const T* w_base = sW + slot * GBK;
     const int rows = (int)min((int64_t)GBK, nrows - kt * GBK);
-    if (rows == GBK) {
+    if (half && (int)(kt & 1) != my_parity) {
+      // not this warp's stage
+    } else if (rows == GBK) {
 #pragma unroll
       for (int kk = 0; kk < GBK / 4; ++kk) {
         const int k = kk * 4 + q;
@@ -366,6 +377,34 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
     if (lane == 0) mbar_arrive(empty + slot);
   }
   compute_barrier();   // every stage consumed by every compute warp: the ring can be reused as the epilogue tile
+
+  if (diag) {
+    // merge the helpers' partial accumulators into the owners' (warp 4 -> 6, warp 5 -> 7)
+    double* hbuf = reinterpret_cast<double*>(smem_raw);          // [2][GACC][32]
+    if (helper) {
+      double* dst = hbuf + (size_t)wn * GACC * 32 + lane;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dst[((t * 4 + u) * 2 + 0) * 32] = acc[t][u][0];
+          dst[((t * 4 + u) * 2 + 1) * 32] = acc[t][u][1];
+          acc[t][u][0] = acc[t][u][1] = 0.0;                     // the helper's own tile is below the diagonal
+        }
+    }
+    compute_barrier();
+    if (half && !helper) {
+      const double* src = hbuf + (size_t)(wn - 2) * GACC * 32 + lane;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[t][u][0] += src[((t * 4 + u) * 2 + 0) * 32];
+          acc[t][u][1] += src[((t * 4 + u) * 2 + 1) * 32];
+        }
+    }
+    compute_barrier();
+  }
 
   if (unit.nsplit == 1 && !p.force_partials) {
     gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
