@@ -88,3 +88,33 @@ class ShardedFolds:
         _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
                                            vp(out["scal"]), vp(out["status"])), h)
         return dict(out, fold_begin=o0, fold_end=o1)
+
+
+def fit_row_sharded(cvm: CVMatrix, X, Y=None, weights=None, group=None) -> None:
+    """
+    ``cvm.fit`` with the Gram pass (X^T W [X|Y], the 2 N K (K+M) flops of fit) split by rows across the ranks of
+    ``group``: every rank uploads the data (it needs all rows for its folds anyway), contracts only its row slab and
+    the partial totals are combined with ONE all-reduce over NVLink (K x ld elements: 2 MB at K = 500).  The moment
+    sums keep numpy's sequential order, so every rank computes them over all rows.  float64 partial sums are added
+    by NCCL in ring / tree order, so the totals can differ from the single-GPU ones in the last bits.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = np.asarray(X).shape[0]
+    r0, r1 = sharding.fold_block(rank, world, 0, n)
+    cvm.fit(X, Y, weights, _gram_rows=(r0, r1))
+    if world == 1:
+        return
+    lib, h = cvm._lib, cvm._h
+    ptr, count, ld = C.c_void_p(), C.c_int64(), C.c_int64()
+    _lib.check(lib.cvmx_totals_ptr(h, C.byref(ptr), C.byref(count), C.byref(ld)), h)
+    f64 = np.dtype(cvm.dtype) == np.float64
+    tot = torch.as_tensor(_DevArray(ptr.value, count.value, "<f8" if f64 else "<f4"), device=torch.device("cuda", cvm.device))
+    _lib.check(lib.cvmx_sync(h), h)
+    dist.all_reduce(tot, group=group)
+    torch.cuda.synchronize(cvm.device)
+    _lib.check(lib.cvmx_commit_totals(h), h)
+    cvm._pull_totals()

@@ -1,0 +1,51 @@
+"""Worker of tests/test_gpu_multi.py: row-sharded fit + fold-sharded / row-sharded fold batches on WORLD_SIZE GPUs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ctypes as C  # noqa: E402
+
+from cvmatrix_b200 import CVMatrix, Partitioner, _lib  # noqa: E402
+from cvmatrix_b200.distributed import ShardedFolds, fit_row_sharded  # noqa: E402
+from cvmatrix_oracle import OracleCVMatrix, make_inputs, rel_fro  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+X, Y, w, folds = make_inputs(60_000, 200, 6, 3, seed=13)
+orc = OracleCVMatrix()
+orc.fit(X, Y, w)
+m = CVMatrix(device=local)
+fit_row_sharded(m, X, Y, w)
+assert rel_fro(m.XTX, orc.XTX) <= 1e-14 and rel_fro(m.XTY, orc.XTY) <= 1e-14
+assert np.array_equal(m.sum_X, orc.sum_X) and m.sum_w == orc.sum_w
+part = Partitioner(folds)
+m.set_folds(part)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+_lib.check(m._lib.cvmx_set_stream(m._h, C.c_void_p(stream.cuda_stream)), m._h)
+sf = ShardedFolds(m)
+for row_sharded in (True, False):
+    out = sf.training_batch(0, 3, row_sharded=row_sharded)
+    torch.cuda.synchronize()
+    for pos, f in enumerate(range(out["fold_begin"], out["fold_end"])):
+        r = orc.fold(part.get_validation_indices(f))
+        K = 200
+        assert rel_fro(out["XTX"][pos].cpu().numpy(), r.XTX) <= 1e-12, (row_sharded, f)
+        assert rel_fro(out["XTY"][pos].cpu().numpy(), r.XTY) <= 1e-12, (row_sharded, f)
+        assert np.array_equal(out["stats"][pos, 0, :K].cpu().numpy(), r.X_mean[0]), (row_sharded, f)
+        assert np.array_equal(out["stats"][pos, 1, K:].cpu().numpy(), r.Y_std[0]), (row_sharded, f)
+owned = torch.zeros(3, device="cuda")
+owned[out["fold_begin"]:out["fold_end"]] += 1
+dist.all_reduce(owned)
+assert bool((owned == 1).all())
+dist.barrier()
+if rank == 0:
+    print("DIST_OK", world)
+dist.destroy_process_group()
