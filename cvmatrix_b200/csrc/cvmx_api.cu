@@ -415,10 +415,22 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   // rate), re-pitch each into Z with a kernel, and run the chunk's share of the Gram pass and of the moment chains
   // right behind it, so that fit costs little more than the host->device copy.
   const bool chunked = N > 0 && mem == CVMX_HOST && ldx == K && K > 1 && (size_t)N * K * sz >= ((size_t)64 << 20);
+  // a pitch-changing 2-D copy of a narrow matrix (Y: 80-byte rows) is one DMA descriptor per row - ~20 ms for 1M rows -
+  // so in the chunked path Y is copied contiguously into a scratch buffer and re-pitched by a kernel
+  const bool stage_y = chunked && M > 0 && ldy == M;
   if (N > 0) {
-    if (ld > K + M) CU(h, cudaMemset2DAsync(Z + (K + M), ld * sz, 0, (ld - K - M) * sz, N, h->stream));
+    if (ld > K + M) {
+      if (chunked) { k_zero_pad<T><<<h->sm_count * 4, 256, 0, h->stream>>>(Z, N, ld, K + M); h->launches++; }
+      else CU(h, cudaMemset2DAsync(Z + (K + M), ld * sz, 0, (ld - K - M) * sz, N, h->stream));
+    }
     if (!chunked) CU(h, cudaMemcpy2DAsync(Z, ld * sz, X, ldx * sz, K * sz, N, kind, h->stream));
-    if (M > 0) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
+    if (M > 0 && !stage_y) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
+    if (stage_y) {
+      CU(h, h->out_xy.reserve((size_t)N * M * sz));   // scratch (reused by host-output fold batches later)
+      CU(h, cudaMemcpyAsync(h->out_xy.p, Y, (size_t)N * M * sz, cudaMemcpyHostToDevice, h->stream));
+      k_repack<T><<<h->sm_count * 4, 256, 0, h->stream>>>(h->out_xy.as<T>(), N, M, Z + K, ld);
+      h->launches++;
+    }
     if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
     else { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
   }
@@ -525,6 +537,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
       k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>(h->stage[b].as<T>(), nr, K, Z + r0 * ld, ld);
       h->launches++;
+
       CU(h, cudaEventRecord(h->ev_stage[b], h->stream));
       // the chunk's rows of the moment chains, continuing the accumulators of the previous chunk
       CU(h, cudaStreamWaitEvent(stats_stream, h->ev_stage[b], 0));

@@ -485,6 +485,17 @@ __global__ void k_repack(const T* __restrict__ src, int64_t rows, int64_t cols, 
   }
 }
 
+// Zero the pad columns [c0, ld) of every row (one thread per pad element).
+template <typename T>
+__global__ void k_zero_pad(T* __restrict__ Z, int64_t rows, int64_t ld, int64_t c0) {
+  const int64_t w = ld - c0;
+  const int64_t total = rows * w;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / w, c = e - r * w;
+    Z[r * ld + c0 + c] = T(0);
+  }
+}
+
 template <typename T>
 __global__ void k_fill(T* __restrict__ p, int64_t n, T v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
