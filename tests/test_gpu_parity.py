@@ -431,3 +431,30 @@ def test_many_folds_exceed_one_grid_dimension():
         assert rel_fro(out["XTX"][f], r.XTX) <= 1e-12 and rel_fro(out["XTY"][f], r.XTY) <= 1e-12
         assert np.array_equal(out["X_mean"][f], r.X_mean) and np.array_equal(out["Y_std"][f], r.Y_std)
     assert int(out["status"].max()) == 0
+
+
+def test_cuda_path_equals_naive_recomputation():
+    """Second oracle, independent of the downdating algorithm: training-set matrices recomputed from the training rows
+    (the reference's fast-vs-naive test strategy, atol = 1e-8), all 16 flag combinations, batched launch."""
+    import itertools
+
+    from naive_oracle import naive_training_matrices
+
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    X, Y, w, folds = make_inputs(5000, 140, 5, 4, seed=33)
+    w[::11] = 0
+    part = Partitioner(folds)
+    for flags in itertools.product((False, True), repeat=4):
+        m = CVMatrix(*flags)
+        m.fit(X, Y, w)
+        m.set_folds(part)
+        out = m.training_batch()
+        for f in (0, 3):
+            n = naive_training_matrices(X, Y, w, part.get_validation_indices(f), *flags)
+            np.testing.assert_allclose(out["XTX"][f], n["XTX"], atol=1e-8, rtol=1e-9)
+            np.testing.assert_allclose(out["XTY"][f], n["XTY"], atol=1e-8, rtol=1e-9)
+            if out["X_std"] is not None:
+                np.testing.assert_allclose(out["X_std"][f], n["X_std"], atol=1e-10)
+            if out["Y_mean"] is not None:
+                np.testing.assert_allclose(out["Y_mean"][f], n["Y_mean"], atol=1e-10)

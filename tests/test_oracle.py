@@ -142,3 +142,28 @@ def test_oracle_pinned_to_live_reference():
     script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "check_against_reference.py")
     r = subprocess.run([sys.executable, script], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_downdating_oracle_equals_naive_recomputation():
+    """The reference's own test strategy (tests/test_cvmatrix.py:420-575): fast == naive for all 16 flag combinations,
+    weighted (with zero weights) and unweighted, atol = 1e-8."""
+    import itertools
+
+    from cvmatrix_oracle import make_inputs
+    from naive_oracle import naive_training_matrices
+
+    X, Y, w, folds = make_inputs(700, 9, 3, 3, seed=31)
+    w[::7] = 0
+    for flags in itertools.product((False, True), repeat=4):
+        for weights in (w, None):
+            o = OracleCVMatrix(*flags)
+            o.fit(X, Y, weights)
+            for f in range(3):
+                val = np.flatnonzero(folds == f)
+                r = o.fold(val)
+                n = naive_training_matrices(X, Y, weights, val, *flags)
+                np.testing.assert_allclose(r.XTX, n["XTX"], atol=1e-8)
+                np.testing.assert_allclose(r.XTY, n["XTY"], atol=1e-8)
+                for name, got in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
+                    if got is not None:
+                        np.testing.assert_allclose(got, n[name], atol=1e-10)
