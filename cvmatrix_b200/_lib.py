@@ -41,6 +41,8 @@ SIGNATURES = {
     "cvmx_partition_labels": (_i64, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cvmx_launch_count": (_i64, [_vp]),
     "cvmx_ld": (_i64, [_vp]),
+    "cvmx_set_scan_mode": (_i32, [_vp, _i32]),
+    "cvmx_scan_launch_count": (_i64, [_vp]),
 }
 
 _lib = None

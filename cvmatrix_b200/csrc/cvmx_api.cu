@@ -9,6 +9,9 @@
 #include "../../include/cvmx.h"
 #include "kernels_gram.cuh"
 #include "kernels_stats.cuh"
+#include "kernels_scan.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 using namespace cvmx;
 
@@ -69,6 +72,11 @@ struct cvmx_handle {
   DevBuf units, tiles, fold_units, split_folds, partials, stats, rawsums, fscal, pwcols, errflag, out_xx, out_xy, out_small;
   Plan plan;
   bool attr_gram = false, attr_mom = false;
+  // binade scan of the moment chains (kernels_scan.cuh): 0 off, 1 when the chains are the critical path, 2 always
+  int scan_mode = 1;
+  DevBuf scan_seg, scan_ok, scan_list, scan_cnt;
+  bool attr_scan = false;
+  int64_t scan_launches = 0;
   int64_t launches = 0;
   // optional per-kernel timing (cvmx_profile_*): event pairs recorded on the handle stream
   bool prof = false;
@@ -271,7 +279,8 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
 }
 
 template <typename T>
-int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard = 0, int n_col_shards = 1) {
+int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard = 0, int n_col_shards = 1,
+                       double overlap_ns = 1e30) {
   if (!h->attr_mom) {
     CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)moments_pipe_smem<T>(MOM_STAGES_DEEP)));
@@ -286,6 +295,15 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     mp.stages = (mine0 * nfolds <= 32 && max_rows >= 4096) ? MOM_STAGES_DEEP : MOM_STAGES;
   }
   const size_t smem = moments_pipe_smem<T>(mp.stages);
+  // float64 chains that nothing hides (overlap_ns: device time of the work running beside them; a chain costs
+  // ~7.6 ns per row) go through the binade scan; groups it cannot handle fall through to k_moments_pipe below
+  bool scan = false;
+  const int64_t max_segs = round_up((max_rows + SCAN_L - 1) / SCAN_L, SCAN_PER_LANE);
+  if (std::is_same<T, double>::value && pipe && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
+    const size_t seg_bytes = (size_t)std::min<int64_t>(65535, nfolds) * max_segs * 4 * mp.ld * sizeof(double);
+    scan = seg_bytes <= ((size_t)2 << 30) &&
+           (h->scan_mode == 2 ? max_rows >= 4 * SCAN_L : (max_rows >= 8192 && 7.6 * (double)max_rows > 0.7 * overlap_ns));
+  }
   for (int64_t f0 = 0; f0 < nfolds; f0 += 65535) {
     const unsigned ny = (unsigned)std::min<int64_t>(65535, nfolds - f0);
     MomentParams<T> q = mp;
@@ -300,6 +318,30 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     const int64_t groups = pipe ? mp.ld / MOM_COLS : (mp.ld + 127) / 128;
     const int64_t mine = groups > col_shard ? (groups - col_shard + n_col_shards - 1) / n_col_shards : 0;
     if (mine == 0) continue;
+    if constexpr (std::is_same<T, double>::value) {
+      if (scan) {
+        ScanParams sp;
+        sp.p = q; sp.L = SCAN_L; sp.max_segs = max_segs; sp.groups_total = (int)groups;
+        CU(h, h->scan_seg.reserve((size_t)ny * max_segs * 4 * mp.ld * sizeof(double)));
+        CU(h, h->scan_ok.reserve((size_t)ny * groups * sizeof(int)));
+        sp.slow_cap = (int)(max_segs / 4 + 2);
+        CU(h, h->scan_list.reserve((size_t)ny * 2 * sp.slow_cap * mp.ld * sizeof(int)));
+        CU(h, h->scan_cnt.reserve((size_t)ny * 2 * mp.ld * sizeof(int)));
+        sp.seg = h->scan_seg.as<double>(); sp.ok = h->scan_ok.as<int>();
+        sp.slow_list = h->scan_list.as<int>(); sp.slow_cnt = h->scan_cnt.as<int>();
+        if (!h->attr_scan) {
+          CU(h, cudaFuncSetAttribute(k_scan_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_CHAIN_SMEM));
+          h->attr_scan = true;
+        }
+        const dim3 gseg((unsigned)mine, (unsigned)((max_segs + SCAN_WARPS - 1) / SCAN_WARPS), ny);
+        k_scan_segsums<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+        k_scan_prefix<<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp);
+        k_scan_delta<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+        k_scan_chain<<<dim3((unsigned)(mine * (SCAN_COLS / SCAN_CHAIN_COLS)), ny), SCAN_CHAIN_THREADS, SCAN_CHAIN_SMEM, h->stream>>>(sp);
+        h->launches += 4; h->scan_launches += 1;
+        q.scan_ok = sp.ok; q.scan_groups = sp.groups_total;
+      }
+    }
     if (pipe) k_moments_pipe<T><<<dim3((unsigned)mine, ny), MOM_THREADS, smem, h->stream>>>(q);
     else k_moments_direct<T><<<dim3((unsigned)mine, ny), 128, 0, h->stream>>>(q);
     h->launches++;
@@ -328,7 +370,7 @@ int32_t join_stats(cvmx_t* h, cudaStream_t saved) {
 // concurrently - the chains store raw sums - and k_finalize_stats turns them into means / stds once both are done.
 template <typename T>
 int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, int64_t max_rows,
-                          int col_shard, int n_col_shards) {
+                          int col_shard, int n_col_shards, double overlap_ns) {
   const size_t sz = sizeof(T);
   const int64_t ld = h->ld;
   CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
@@ -363,7 +405,7 @@ int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx,
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
   mp.raw = h->rawsums.as<T>();
-  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards);
+  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards, overlap_ns);
   if (rc) return rc;
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0));
   mp.grp0 = 0; mp.grp_stride = 1;
@@ -464,7 +506,8 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   h->launches++;
   int32_t rc = CVMX_OK;
   if (!chunked) {
-    rc = launch_moments<T>(h, mp, 1, N);
+    // the Gram pass that runs beside the chains: ~2 (g1 - g0) K (K + M) flops at ~40 TFLOP/s
+    rc = launch_moments<T>(h, mp, 1, N, 0, 1, 2.0 * (double)(g1 - g0) * (double)K * (double)(K + M) / 4e4);
     if (rc) { h->stream = main_stream; return rc; }
     rc = join_stats(h, main_stream);
     if (rc) return rc;
@@ -608,7 +651,9 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     if (rc) return rc;
   }
   {
-    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1);
+    // device time the chains can hide behind: the Gram kernel when it overlaps them, nothing otherwise
+    const double gram_ns = 2.0 * (double)(off[f1] - off[f0]) * (double)K * (double)(K + M) / 4e4;
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1, overlap ? gram_ns : 0.0);
     if (rc) { h->stream = main_stream; return rc; }
   }
   if (overlap) {
@@ -643,7 +688,9 @@ int32_t sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int col_shard, int n_co
   cudaStream_t main_stream;
   int32_t rc0 = fork_stats(h, &main_stream);
   if (rc0) return rc0;
-  int32_t rc = launch_fold_stats<T>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, Pn, max_rows, col_shard, n_col_shards);
+  // phase 2 (this rank's row shard of the Gram pass) runs beside the chains
+  const double gram_ns = 2.0 * (double)(h->h_off[f1] - h->h_off[f0]) * (double)h->K * (double)(h->K + h->M) / 4e4 / n_col_shards;
+  int32_t rc = launch_fold_stats<T>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, Pn, max_rows, col_shard, n_col_shards, gram_ns);
   int32_t rc2 = join_stats(h, main_stream);
   return rc ? rc : rc2;
 }
@@ -879,6 +926,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   cvmx_t* h = new cvmx_handle();
   h->device = device; h->dtype = dtype; h->flags = flags & 15u; h->ddof = ddof; h->resolution = resolution;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
     return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
@@ -908,7 +956,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
-                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small})
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
@@ -1143,6 +1191,12 @@ int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int6
 }
 
 int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }
+int64_t cvmx_scan_launch_count(const cvmx_t* h) { return h ? h->scan_launches : 0; }
+int32_t cvmx_set_scan_mode(cvmx_t* h, int32_t mode) {
+  if (!h || mode < 0 || mode > 2) return fail(h, CVMX_ERR_INVALID, "cvmx_set_scan_mode: mode must be 0, 1 or 2");
+  h->scan_mode = mode;
+  return CVMX_OK;
+}
 int64_t cvmx_ld(const cvmx_t* h) { return h ? h->ld : 0; }
 
 }  // extern "C"

@@ -226,6 +226,8 @@ struct MomentParams {
   int stages = 4;               // ring depth of k_moments_pipe (runtime: few long chains want more bytes in flight)
   int64_t row0 = 0;             // fit mode: rows [row0, row0 + N) ...
   int accumulate = 0;           // ... continuing the chains stored in sum_z / sumsq_z (chunk-pipelined fit)
+  const int* scan_ok = nullptr; // [folds][scan_groups]: groups already finished by the binade scan (kernels_scan.cuh);
+  int scan_groups = 0;          // k_moments_pipe skips them
 };
 
 template <typename T>
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   uint64_t* empty = full + NST;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f = blockIdx.y;
+  if (p.scan_ok && p.scan_ok[f * p.scan_groups + (p.grp0 + blockIdx.x * p.grp_stride)]) return;   // whole CTA
   const int64_t c0 = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * MOM_COLS;
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;

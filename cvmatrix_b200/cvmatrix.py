@@ -415,6 +415,16 @@ class CVMatrix:
     def sync(self) -> None:
         _lib.check(self._lib.cvmx_sync(self._h), self._h)
 
+    def set_scan_mode(self, mode: int) -> None:
+        """How float64 column sums in numpy's sequential order are evaluated (include/cvmx.h, cvmx_set_scan_mode):
+        0 dependent-add chains only, 1 (default) the bit-identical binade scan when the chains are on the critical
+        path, 2 the scan whenever a fold has >= 1024 rows."""
+        _lib.check(self._lib.cvmx_set_scan_mode(self._h, int(mode)), self._h)
+
+    @property
+    def scan_launch_count(self) -> int:
+        return int(self._lib.cvmx_scan_launch_count(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.cvmx_launch_count(self._h))

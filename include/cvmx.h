@@ -177,6 +177,14 @@ int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int6
 int64_t cvmx_launch_count(const cvmx_t* h);
 int64_t cvmx_ld(const cvmx_t* h);
 
+/* Column sums in numpy's order (np.sum(A, axis=0): sequential per column, cvmatrix/cvmatrix.py:709, 716, 727, 737,
+ * 1231-1241) are evaluated either as dependent-add chains or, for float64, by the bit-identical "binade scan"
+ * (csrc/kernels_scan.cuh).  mode 0: chains only; 1 (default): scan when the chains are on the critical path;
+ * 2: scan whenever a fold has >= 1024 rows.  Also settable with the environment variable CVMX_SCAN at cvmx_create.
+ * cvmx_scan_launch_count: how many moment launches went through the scan so far. */
+int32_t cvmx_set_scan_mode(cvmx_t* h, int32_t mode);
+int64_t cvmx_scan_launch_count(const cvmx_t* h);
+
 #ifdef __cplusplus
 }
 #endif
