@@ -25,6 +25,11 @@ SIGNATURES = {
     "cvmx_set_stream": (_i32, [_vp, _vp]),
     "cvmx_sync": (_i32, [_vp]),
     "cvmx_fit": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _i64, _i64]),
+    "cvmx_fit_begin": (_i32, [_vp, _i64, _i64, _i64, _i32, _i64]),
+    "cvmx_fit_rows": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32]),
+    "cvmx_fit_end": (_i32, [_vp, _i32, _i32]),
+    "cvmx_data_ptr": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "cvmx_moments_ptr": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "cvmx_totals_ptr": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "cvmx_commit_totals": (_i32, [_vp]),
     "cvmx_get_totals": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i64)]),

@@ -74,6 +74,10 @@ struct cvmx_handle {
   bool attr_gram = false, attr_mom = false;
   // binade scan of the moment chains (kernels_scan.cuh): 0 off, 1 when the chains are the critical path, 2 always
   int scan_mode = 1;
+  // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
+  bool filling = false;
+  int64_t fill_units_cap = 0, fill_calls = 0;
+  DevBuf ystage;
   DevBuf scan_seg, scan_ok, scan_list, scan_cnt;
   bool attr_scan = false;
   int64_t scan_launches = 0;
@@ -295,14 +299,24 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     mp.stages = (mine0 * nfolds <= 32 && max_rows >= 4096) ? MOM_STAGES_DEEP : MOM_STAGES;
   }
   const size_t smem = moments_pipe_smem<T>(mp.stages);
-  // float64 chains that nothing hides (overlap_ns: device time of the work running beside them; a chain costs
-  // ~7.6 ns per row) go through the binade scan; groups it cannot handle fall through to k_moments_pipe below
+  // float64 chains go through the binade scan when that is faster AND the chains are not hidden anyway
+  // (overlap_ns: device time of the work running beside them).  Cost model (measured, profiles/): a chain CTA
+  // needs ~7.6 ns per row and 3 of them share an SM; both variants are bounded by HBM traffic (the scan reads the
+  // rows twice, at ~5 TB/s) and the scan has ~0.15 ms of serial passes.  Groups the scan cannot handle fall
+  // through to k_moments_pipe below.
   bool scan = false;
   const int64_t max_segs = round_up((max_rows + SCAN_L - 1) / SCAN_L, SCAN_PER_LANE);
   if (std::is_same<T, double>::value && pipe && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
     const size_t seg_bytes = (size_t)std::min<int64_t>(65535, nfolds) * max_segs * 4 * mp.ld * sizeof(double);
+    const int64_t groups0 = mp.ld / MOM_COLS;
+    const int64_t mine0 = groups0 > col_shard ? (groups0 - col_shard + n_col_shards - 1) / n_col_shards : 0;
+    const double ctas = (double)mine0 * (double)nfolds;
+    const double bytes = ctas * (double)max_rows * MOM_COLS * sizeof(double);
+    const double waves = std::ceil(ctas / (3.0 * h->sm_count));
+    const double pipe_ns = std::max(7.6 * (double)max_rows * waves, bytes / 6000.0);
+    const double scan_ns = 2.0 * bytes / 5000.0 + 150e3;
     scan = seg_bytes <= ((size_t)2 << 30) &&
-           (h->scan_mode == 2 ? max_rows >= 4 * SCAN_L : (max_rows >= 8192 && 7.6 * (double)max_rows > 0.7 * overlap_ns));
+           (h->scan_mode == 2 ? max_rows >= 4 * SCAN_L : (max_rows >= 8192 && scan_ns < pipe_ns && pipe_ns > 0.7 * overlap_ns));
   }
   for (int64_t f0 = 0; f0 < nfolds; f0 += 65535) {
     const unsigned ny = (unsigned)std::min<int64_t>(65535, nfolds - f0);
@@ -621,6 +635,183 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   FitScalars fsc;
   CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  if (fsc.neg_weight) return fail(h, CVMX_ERR_NEG_WEIGHT, "Weights must be non-negative.");
+  h->fitted = true;
+  return CVMX_OK;
+}
+
+
+// ---- streaming / sharded fit -------------------------------------------------------------------------------
+// cvmx_fit in pieces: the caller feeds row blocks (host or device memory, any order, possibly only a slab of the
+// rows - the rest may arrive from peer GPUs over NVLink, written straight into cvmx_data_ptr()), each block's
+// weighted Gram is folded into a float64 accumulator in fragment layout (partial slot 0), and cvmx_fit_end turns
+// the accumulator into the totals and runs the numpy-order statistics over all N rows.
+int64_t fill_units_for(const cvmx_t* h, int64_t rows, int ntiles) {
+  const int64_t by_ws = std::max<int64_t>(1, (int64_t)(((size_t)2 << 30) / ((size_t)std::max(ntiles, 1) * GACC * GTHREADS * sizeof(double))) - 1);
+  int64_t nu = std::max<int64_t>(1, (rows + 2815) / 2816);
+  // wide K: the tiles alone fill the GPU; keep the units long
+  if ((int64_t)ntiles >= h->sm_count) nu = std::max<int64_t>(1, std::min<int64_t>(nu, (rows + 16383) / 16384 * 2));
+  return std::min(nu, by_ws);
+}
+
+template <typename T>
+int32_t fit_begin_impl(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weighted, int64_t max_block_rows) {
+  const size_t sz = sizeof(T);
+  const int64_t ld = round_up(K + M, 32);
+  h->fitted = false; h->filling = false;
+  h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = weighted != 0;
+  h->P = 0; h->csr_version++; h->plan = Plan();
+  CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
+  CU(h, h->w.reserve((size_t)std::max<int64_t>(N, 1) * sz));
+  CU(h, h->Ttot.reserve((size_t)K * ld * sz));
+  CU(h, h->sum_z.reserve(ld * sz));
+  CU(h, h->sumsq_z.reserve(ld * sz));
+  CU(h, h->fit_scal.reserve(sizeof(FitScalars)));
+  CU(h, h->pwcols.reserve(4 * sz));
+  std::vector<int2> tiles;
+  plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), tiles);
+  const int ntiles = (int)tiles.size();
+  h->fill_units_cap = fill_units_for(h, std::max<int64_t>(max_block_rows, 1), ntiles);
+  const size_t slot = (size_t)ntiles * GACC * GTHREADS * sizeof(double);
+  CU(h, h->partials.reserve((size_t)(h->fill_units_cap + 1) * slot));
+  CU(h, h->tiles.reserve(tiles.size() * sizeof(int2)));
+  CU(h, h->units.reserve((size_t)(h->fill_units_cap + 1) * sizeof(GramUnit)));
+  CU(h, h->fold_units.reserve(sizeof(int32_t)));
+  CU(h, h->split_folds.reserve(sizeof(int32_t)));
+  CU(h, cudaMemcpyAsync(h->tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->partials.p, 0, slot, h->stream));                  // the accumulator
+  CU(h, cudaMemsetAsync(h->fold_units.p, 0, sizeof(int32_t), h->stream));
+  CU(h, cudaMemsetAsync(h->split_folds.p, 0, sizeof(int32_t), h->stream));
+  CU(h, cudaMemsetAsync(h->Ttot.p, 0, (size_t)K * ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->sum_z.p, 0, ld * sz, h->stream));
+  CU(h, cudaMemsetAsync(h->sumsq_z.p, 0, ld * sz, h->stream));
+  if (!weighted && N > 0) { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
+  const size_t smem = gram_smem_bytes<T>();
+  if (!h->attr_gram) {
+    CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(h, cudaFuncSetAttribute(k_gram_reduce<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->attr_gram = true;
+  }
+  CU(h, cudaStreamSynchronize(h->stream));   // `tiles` is a local
+  h->filling = true; h->fill_calls = 0;
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t fit_rows_impl(cvmx_t* h, int64_t row0, int64_t nr, const void* X, int64_t ldx, const void* Y, int64_t ldy, const void* w,
+                      int32_t mem, int32_t gram) {
+  const size_t sz = sizeof(T);
+  const int64_t K = h->K, M = h->M, ld = h->ld;
+  T* Zb = h->Z.as<T>() + (size_t)row0 * ld;
+  const int cb = (int)(h->fill_calls & 1);
+  h->fill_calls++;
+  if (ld > K + M) { k_zero_pad<T><<<h->sm_count * 4, 256, 0, h->stream>>>(Zb, nr, ld, K + M); h->launches++; }
+  if (mem == CVMX_HOST) {
+    // contiguous copies at full PCIe rate into a staging buffer on the copy stream (they overlap the Gram of the
+    // previous block on the main stream), re-pitched into Z by a kernel; strided inputs fall back to 2-D copies
+    const bool cx = ldx == K, cy = M > 0 && ldy == M;
+    const size_t xb = cx ? (size_t)nr * K * sz : 0, yb = cy ? (size_t)nr * M * sz : 0;
+    CU(h, h->stage[cb].reserve(std::max<size_t>(xb + yb, 16)));
+    CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[cb], 0));      // the kernels that read this buffer two calls ago
+    char* st = h->stage[cb].as<char>();
+    if (cx) CU(h, cudaMemcpyAsync(st, X, xb, cudaMemcpyHostToDevice, h->aux2_stream));
+    else CU(h, cudaMemcpy2DAsync(Zb, ld * sz, X, ldx * sz, K * sz, nr, cudaMemcpyHostToDevice, h->aux2_stream));
+    if (cy) CU(h, cudaMemcpyAsync(st + xb, Y, yb, cudaMemcpyHostToDevice, h->aux2_stream));
+    else if (M > 0) CU(h, cudaMemcpy2DAsync(Zb + K, ld * sz, Y, ldy * sz, M * sz, nr, cudaMemcpyHostToDevice, h->aux2_stream));
+    if (h->weighted) CU(h, cudaMemcpyAsync(h->w.as<T>() + row0, w, nr * sz, cudaMemcpyHostToDevice, h->aux2_stream));
+    CU(h, cudaEventRecord(h->ev_copied[cb], h->aux2_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[cb], 0));
+    if (cx) { k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>((const T*)st, nr, K, Zb, ld); h->launches++; }
+    if (cy) { k_repack<T><<<h->sm_count * 4, 256, 0, h->stream>>>((const T*)(st + xb), nr, M, Zb + K, ld); h->launches++; }
+    CU(h, cudaEventRecord(h->ev_stage[cb], h->stream));
+  } else {
+    if (ldx == K) { k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>((const T*)X, nr, K, Zb, ld); h->launches++; }
+    else CU(h, cudaMemcpy2DAsync(Zb, ld * sz, X, ldx * sz, K * sz, nr, cudaMemcpyDeviceToDevice, h->stream));
+    if (M > 0 && ldy == M) { k_repack<T><<<h->sm_count * 4, 256, 0, h->stream>>>((const T*)Y, nr, M, Zb + K, ld); h->launches++; }
+    else if (M > 0) CU(h, cudaMemcpy2DAsync(Zb + K, ld * sz, Y, ldy * sz, M * sz, nr, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->weighted) CU(h, cudaMemcpyAsync(h->w.as<T>() + row0, w, nr * sz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  // the caller may reuse its block buffers on return: host blocks are free once the copies above are done (the
+  // Gram of this block then overlaps the next block's upload); device blocks are read by kernels on this stream
+  if (!gram) {
+    if (mem == CVMX_HOST) CU(h, cudaEventSynchronize(h->ev_copied[cb]));
+    else CU(h, cudaStreamSynchronize(h->stream));
+    return CVMX_OK;
+  }
+
+  std::vector<int2> tiles;
+  plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), tiles);
+  const int ntiles = (int)tiles.size();
+  const int64_t nu = std::min(h->fill_units_cap, fill_units_for(h, nr, ntiles));
+  const int64_t per = round_up((nr + nu - 1) / nu, GBK);
+  std::vector<GramUnit> units(nu + 1);
+  units[0].row_begin = units[0].row_end = 0; units[0].fold = 0; units[0].split = 0; units[0].nsplit = (int32_t)(nu + 1); units[0].part_base = 0;
+  for (int64_t u = 0; u < nu; ++u) {
+    GramUnit& g = units[u + 1];
+    g.row_begin = row0 + std::min(nr, u * per); g.row_end = row0 + std::min(nr, (u + 1) * per);
+    g.fold = 0; g.split = (int32_t)(u + 1); g.nsplit = (int32_t)(nu + 1); g.part_base = 0;
+  }
+  CU(h, cudaMemcpyAsync(h->units.p, units.data(), units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  GramParams<T> gp;
+  gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
+  gp.units = h->units.as<GramUnit>() + 1; gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.partials = h->partials.as<double>(); gp.raw_out = nullptr; gp.force_partials = 1;
+  gp.epi = EpiParams<T>();
+  const size_t smem = gram_smem_bytes<T>();
+  const int ev0 = prof_mark(h);
+  k_gram<T><<<(unsigned)(nu * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+  const int ev1 = prof_mark(h);
+  prof_span(h, PROF_GRAM, ev0, ev1);
+  // accumulator (slot 0) += the block's partials, in place
+  gp.units = h->units.as<GramUnit>(); gp.raw_out = h->partials.as<double>();
+  k_gram_reduce<T><<<dim3(ntiles, 1), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
+  h->launches += 2;
+  CU(h, cudaGetLastError());
+  if (mem == CVMX_HOST) CU(h, cudaEventSynchronize(h->ev_copied[cb]));
+  else CU(h, cudaStreamSynchronize(h->stream));
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
+  const int64_t N = h->N, K = h->K, M = h->M, ld = h->ld;
+  // accumulator -> totals (raw epilogue: mirrored XtWX, XtWY)
+  std::vector<int2> tiles;
+  plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), tiles);
+  const int ntiles = (int)tiles.size();
+  GramUnit v;
+  v.row_begin = v.row_end = 0; v.fold = 0; v.split = 0; v.nsplit = 1; v.part_base = 0;
+  CU(h, cudaMemcpyAsync(h->units.p, &v, sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  EpiParams<T> epi;
+  epi.mode = 0; epi.flags = 0; epi.want = CVMX_WANT_XTX | CVMX_WANT_XTY;
+  epi.K = K; epi.M = M; epi.ld = ld;
+  epi.Ttot = nullptr; epi.stats = nullptr; epi.fs = nullptr;
+  epi.out_xx = h->Ttot.as<T>(); epi.xx_pitch = ld; epi.xx_stride = 0;
+  epi.out_xy = h->Ttot.as<T>() + K; epi.xy_pitch = ld; epi.xy_stride = 0;
+  GramParams<T> gp;
+  gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
+  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.partials = h->partials.as<double>(); gp.raw_out = nullptr; gp.force_partials = 0; gp.epi = epi;
+  k_gram_reduce<T><<<dim3(ntiles, 1), GTHREADS, gram_smem_bytes<T>(), h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  h->launches++;
+  CU(h, cudaGetLastError());
+  // statistics over all rows: weight mass everywhere, moment sums for this column shard (others stay zero)
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr,
+                                                                          nullptr, 0, 1, h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
+  h->launches++;
+  MomentParams<T> mp;
+  mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
+  mp.offsets = nullptr; mp.indices = nullptr; mp.fold0 = 0; mp.N = N;
+  mp.flags = h->flags; mp.resolution = (T)h->resolution;
+  mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+  mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
+  int32_t rc = launch_moments<T>(h, mp, 1, N, col_shard, n_col_shards, 0.0);
+  if (rc) return rc;
+  FitScalars fsc;
+  CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->filling = false;
   if (fsc.neg_weight) return fail(h, CVMX_ERR_NEG_WEIGHT, "Weights must be non-negative.");
   h->fitted = true;
   return CVMX_OK;
@@ -956,7 +1147,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
-                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt})
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
@@ -997,6 +1188,50 @@ int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   if (!Y) M = 0;
   return h->dtype == CVMX_F64 ? fit_impl<double>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1)
                               : fit_impl<float>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1);
+}
+
+
+int32_t cvmx_fit_begin(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weighted, int64_t max_block_rows) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  if (N < 0 || K <= 0 || M < 0 || max_block_rows <= 0) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_begin: bad shape arguments");
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64 ? fit_begin_impl<double>(h, N, K, M, weighted, max_block_rows)
+                              : fit_begin_impl<float>(h, N, K, M, weighted, max_block_rows);
+}
+
+int32_t cvmx_fit_rows(cvmx_t* h, int64_t row0, int64_t nrows, const void* X, int64_t ldx, const void* Y, int64_t ldy, const void* w,
+                      int32_t mem, int32_t gram) {
+  if (!h || !h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_rows: call cvmx_fit_begin first");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > h->N || (nrows > 0 && !X) || ldx < h->K || (h->M > 0 && nrows > 0 && (!Y || ldy < h->M)) ||
+      (h->weighted && nrows > 0 && !w))
+    return fail(h, CVMX_ERR_INVALID, "cvmx_fit_rows: bad block arguments");
+  if (nrows == 0) return CVMX_OK;
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64 ? fit_rows_impl<double>(h, row0, nrows, X, ldx, Y, ldy, w, mem, gram)
+                              : fit_rows_impl<float>(h, row0, nrows, X, ldx, Y, ldy, w, mem, gram);
+}
+
+int32_t cvmx_fit_end(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
+  if (!h || !h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end: call cvmx_fit_begin first");
+  if (n_col_shards < 1 || col_shard < 0 || col_shard >= n_col_shards) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end: bad column shard");
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64 ? fit_end_impl<double>(h, col_shard, n_col_shards) : fit_end_impl<float>(h, col_shard, n_col_shards);
+}
+
+int32_t cvmx_data_ptr(cvmx_t* h, void** Z, void** w, int64_t* ld) {
+  if (!h || !(h->filling || h->fitted)) return fail(h, CVMX_ERR_INVALID, "cvmx_data_ptr: no data on the device yet");
+  if (Z) *Z = h->Z.p;
+  if (w) *w = h->w.p;
+  if (ld) *ld = h->ld;
+  return CVMX_OK;
+}
+
+int32_t cvmx_moments_ptr(cvmx_t* h, void** sum_z, void** sumsq_z, int64_t* count) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_moments_ptr: fit first");
+  if (sum_z) *sum_z = h->sum_z.p;
+  if (sumsq_z) *sumsq_z = h->sumsq_z.p;
+  if (count) *count = h->ld;
+  return CVMX_OK;
 }
 
 int32_t cvmx_totals_ptr(cvmx_t* h, void** p, int64_t* count, int64_t* ld) {

@@ -172,6 +172,7 @@ class CVMatrix:
     def fit(self, X: npt.ArrayLike, Y: Optional[npt.ArrayLike] = None, weights: Optional[npt.ArrayLike] = None,
             _gram_rows: Optional[Tuple[int, int]] = None) -> None:
         """cvmatrix/cvmatrix.py:207-328.  Uploads X, Y, weights and computes the dataset-wide totals on the GPU."""
+        self._streamed = False
         self.X = self._init_mat(X)
         self.N, self.K = self.X.shape
         if Y is not None:
@@ -195,6 +196,56 @@ class CVMatrix:
         _lib.check(rc, self._h)
         self._pull_totals()
 
+    # ---- streaming / sharded fit (include/cvmx.h: cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end) -------------------
+    def fit_begin(self, N: int, K: int, M: int = 0, weighted: bool = False, max_block_rows: int = 65536) -> None:
+        """Starts a fit that is fed in row blocks (``fit_rows``) and completed by ``fit_end``: for matrices that are
+        produced on the device, that exceed host memory, or whose upload is shared by several GPUs."""
+        self.X = self.Y = self.weights = None
+        self.N, self.K, self.M = int(N), int(K), (int(M) if M else None)
+        self._partitioner = None
+        self._streamed = False
+        self._stream_weighted = bool(weighted)
+        _lib.check(self._lib.cvmx_fit_begin(self._h, int(N), int(K), int(M or 0), int(bool(weighted)), int(max_block_rows)), self._h)
+
+    @staticmethod
+    def _block(a, dtype):
+        """(pointer, leading dimension, memory kind, keep-alive) of a row block: numpy array or CUDA torch tensor."""
+        if a is None:
+            return None, 0, None, None
+        if hasattr(a, "data_ptr"):   # torch tensor
+            if a.dim() == 1:
+                a = a.reshape(-1, 1)
+            if a.stride(-1) != 1 or (a.dim() == 2 and a.shape[0] > 1 and a.stride(0) < a.shape[1]):
+                a = a.contiguous()
+            if str(a.dtype).split(".")[-1] != np.dtype(dtype).name:
+                raise TypeError(f"block dtype {a.dtype} does not match the model dtype {np.dtype(dtype).name}")
+            ldim = a.stride(0) if (a.dim() == 2 and a.shape[0] > 1) else max(a.shape[-1], 1)
+            return C.c_void_p(a.data_ptr()), int(ldim), (_lib.DEVICE if a.is_cuda else _lib.HOST), a
+        a = np.asarray(a, dtype=dtype)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        a, ldim = CVMatrix._rows(a)
+        return _ptr(a), int(ldim), _lib.HOST, a
+
+    def fit_rows(self, row0: int, X, Y=None, weights=None, gram: bool = True) -> None:
+        """Rows ``[row0, row0 + len(X))`` of the data set: numpy arrays (host) or CUDA torch tensors (device).  With
+        ``gram`` the block's weighted Gram is added to the totals (every row by exactly one rank)."""
+        xp, ldx, mem, kx = self._block(X, self.dtype)
+        yp, ldy, memy, ky = self._block(Y, self.dtype)
+        wp, _, memw, kw = self._block(weights, self.dtype)
+        if (yp is not None and memy != mem) or (wp is not None and memw != mem):
+            raise ValueError("X, Y and weights of a block must live in the same memory (all host or all device)")
+        nrows = int(kx.shape[0])
+        _lib.check(self._lib.cvmx_fit_rows(self._h, int(row0), nrows, xp, ldx, yp, ldy, wp, mem, int(bool(gram))), self._h)
+
+    def fit_end(self, col_shard: int = 0, n_col_shards: int = 1, pull: bool = True) -> None:
+        """Completes a streamed fit.  Multi-GPU callers pass their column shard, all-reduce the totals and moment rows
+        (``distributed.fit_sharded_upload``) and call ``_pull_totals`` themselves."""
+        _lib.check(self._lib.cvmx_fit_end(self._h, int(col_shard), int(n_col_shards)), self._h)
+        self._streamed = True
+        if pull:
+            self._pull_totals()
+
     def _pull_totals(self) -> None:
         dt, K, M = self.dtype, self.K, self.M or 0
         XTX = np.empty((K, K), dt)
@@ -209,7 +260,7 @@ class CVMatrix:
         self.XTX, self.XTY = XTX, XTY
         # gating of the public attributes: cvmatrix/cvmatrix.py:1223-1243
         if cX or cY or sXf or sYf:
-            if self.weights is not None:
+            if self._is_weighted:
                 self.sum_w, self.num_nonzero_w = self.dtype(sum_w.value), int(nnz.value)
             else:
                 self.sum_w, self.num_nonzero_w = self.N, self.N
@@ -260,7 +311,7 @@ class CVMatrix:
     def training_statistics(self, validation_indices: npt.NDArray[np.int_]) -> Stats:
         """cvmatrix/cvmatrix.py:519-574"""
         self._require_fit()
-        has_Y = self.Y is not None
+        has_Y = self._has_Y
         need = (self.center_X or self.scale_X, self.scale_X, (self.center_Y or self.scale_Y) and has_Y, self.scale_Y and has_Y)
         _, _, stats = self._run_indices(validation_indices, _lib.WANT_STATS, need)
         return stats
@@ -270,7 +321,7 @@ class CVMatrix:
         if not return_XTX and not return_XTY:
             raise ValueError(_ERR_NOTHING)
         self._require_fit()
-        if return_XTY and self.Y is None:
+        if return_XTY and not self._has_Y:
             raise ValueError(_ERR_NO_Y)
         cX, cY, sX, sY = self.center_X, self.center_Y, self.scale_X, self.scale_Y
         need = (cX or (return_XTY and cY), sX, return_XTY and (cX or cY), return_XTY and sY)
@@ -280,8 +331,16 @@ class CVMatrix:
             return (XTX, XTY), stats
         return (XTX if return_XTX else XTY), stats
 
+    @property
+    def _has_Y(self) -> bool:
+        return self.Y is not None or (getattr(self, "_streamed", False) and bool(self.M))
+
+    @property
+    def _is_weighted(self) -> bool:
+        return self.weights is not None or (getattr(self, "_streamed", False) and getattr(self, "_stream_weighted", False))
+
     def _require_fit(self):
-        if self.X is None:
+        if self.X is None and not getattr(self, "_streamed", False):
             raise ValueError("fit must be called before the training matrices can be computed")
 
     @staticmethod
@@ -295,7 +354,7 @@ class CVMatrix:
 
     def _raise_for_status(self, status: int, need) -> None:
         any_stat = any(need)
-        if any_stat and self.weights is not None and (status & _lib.FOLD_NO_NONZERO_W):
+        if any_stat and self._is_weighted and (status & _lib.FOLD_NO_NONZERO_W):
             raise ValueError(_ERR_NO_NONZERO)
         if (need[1] or need[3]) and (status & _lib.FOLD_NNZ_LE_DDOF):
             raise ValueError(_ERR_DDOF)
@@ -359,7 +418,7 @@ class CVMatrix:
             fold_end = self._n_folds
         if not return_XTX and not return_XTY:
             raise ValueError(_ERR_NOTHING)
-        if return_XTY and self.Y is None:
+        if return_XTY and not self._has_Y:
             raise ValueError(_ERR_NO_Y)
         P = fold_end - fold_begin
         dt, K, M = self.dtype, self.K, self.M or 0

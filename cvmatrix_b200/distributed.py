@@ -118,3 +118,60 @@ def fit_row_sharded(cvm: CVMatrix, X, Y=None, weights=None, group=None) -> None:
     torch.cuda.synchronize(cvm.device)
     _lib.check(lib.cvmx_commit_totals(h), h)
     cvm._pull_totals()
+
+
+def fit_sharded_upload(cvm: CVMatrix, X, Y=None, weights=None, group=None, block_rows: int = 32768) -> None:
+    """
+    ``cvm.fit`` with the host->device upload AND the Gram pass split by rows across the ranks of ``group``: rank r
+    copies only its own row slab over PCIe (``cvmx_fit_rows``; the slab's Gram runs behind the copy), the slabs are
+    then exchanged over NVLink (one NCCL broadcast per rank, straight into ``cvmx_data_ptr()``), the numpy-order
+    column sums are evaluated per column group (``cvmx_fit_end(rank, world)``: the binade scan) and three
+    all-reduces assemble the totals and the two moment rows.  Every rank ends up with the same fitted state as
+    ``cvm.fit(X, Y, weights)``, having moved 1 / world of the bytes over its PCIe link.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    X = cvm._init_mat(X)
+    Y = cvm._init_mat(Y) if Y is not None else None
+    w = cvm._init_mat(weights).reshape(-1) if weights is not None else None
+    N, K = X.shape
+    M = Y.shape[1] if Y is not None else 0
+    cvm.fit_begin(N, K, M, weighted=w is not None, max_block_rows=block_rows)
+    r0, r1 = sharding.fold_block(rank, world, 0, N)
+    for b0 in range(r0, r1, block_rows):
+        b1 = min(r1, b0 + block_rows)
+        cvm.fit_rows(b0, X[b0:b1], None if Y is None else Y[b0:b1], None if w is None else w[b0:b1], gram=True)
+    lib, h = cvm._lib, cvm._h
+    _lib.check(lib.cvmx_sync(h), h)
+    f64 = np.dtype(cvm.dtype) == np.float64
+    ts = "<f8" if f64 else "<f4"
+    dev = torch.device("cuda", cvm.device)
+    if world > 1:
+        zp, wp, ld = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_data_ptr(h, C.byref(zp), C.byref(wp), C.byref(ld)), h)
+        Z = torch.as_tensor(_DevArray(zp.value, N * ld.value, ts), device=dev)
+        wv = torch.as_tensor(_DevArray(wp.value, N, ts), device=dev)
+        for r in range(world):
+            s0, s1 = sharding.fold_block(r, world, 0, N)
+            if s1 > s0:
+                src = dist.get_global_rank(group, r) if group is not None else r
+                dist.broadcast(Z[s0 * ld.value: s1 * ld.value], src=src, group=group)
+                if w is not None:
+                    dist.broadcast(wv[s0:s1], src=src, group=group)
+        torch.cuda.synchronize(cvm.device)
+    cvm.fit_end(rank, world, pull=False)
+    if world > 1:
+        tp, cnt, ldt = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(lib.cvmx_totals_ptr(h, C.byref(tp), C.byref(cnt), C.byref(ldt)), h)
+        sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_moments_ptr(h, C.byref(sp), C.byref(qp), C.byref(mc)), h)
+        for ptr, count in ((tp, cnt.value), (sp, mc.value), (qp, mc.value)):
+            dist.all_reduce(torch.as_tensor(_DevArray(ptr.value, count, ts), device=dev), group=group)
+        torch.cuda.synchronize(cvm.device)
+        _lib.check(lib.cvmx_commit_totals(h), h)
+    cvm._pull_totals()
+    cvm.X, cvm.Y = X, Y
+    cvm.weights = None if w is None else w.reshape(-1, 1)

@@ -88,6 +88,30 @@ int32_t cvmx_sync(cvmx_t* h);
 int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M,
                  int64_t ldy, const void* w, int32_t mem, int64_t gram_row_begin, int64_t gram_row_end);
 
+/*
+ * The same fit fed in row blocks (streaming / sharded upload), replacing the same reference code as cvmx_fit
+ * (cvmatrix/cvmatrix.py:207-328, 1131-1243).  Use it when the matrix does not exist in one piece on the host (it is
+ * produced on the device, or it is larger than host memory: 180 GB of HBM hold N = 2M x K = 5000 float64), or when
+ * several GPUs share the upload: every rank copies only its own row slab over PCIe and the slabs are exchanged over
+ * NVLink straight into cvmx_data_ptr() (cvmatrix_b200/distributed.py: fit_sharded_upload).
+ *   cvmx_fit_begin : allocates Z = [X | Y | 0-pad] (N x ld), w and the totals; max_block_rows bounds the blocks.
+ *   cvmx_fit_rows  : rows [row0, row0 + nrows) from X (pitch ldx), Y (pitch ldy; ignored when M = 0), w (ignored when
+ *                    unweighted); `mem` = CVMX_HOST or CVMX_DEVICE.  With gram != 0 the block's weighted Gram
+ *                    X^T diag(w) [X | Y] is added to a float64 accumulator; blocks may come in any order, every row
+ *                    must be contracted by exactly one rank.  Returns after the block buffers may be reused.
+ *   cvmx_fit_end   : accumulator -> cvmx_totals_ptr(); sum w / count_nonzero(w) over all N rows (they must all be
+ *                    present by now); numpy-order column sums for column groups col_shard, col_shard + n, ...
+ *                    (others zero).  One GPU: cvmx_fit_end(h, 0, 1) completes the fit.  Several: all-reduce(sum)
+ *                    cvmx_totals_ptr() and cvmx_moments_ptr() across ranks, then cvmx_commit_totals.
+ */
+int32_t cvmx_fit_begin(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weighted, int64_t max_block_rows);
+int32_t cvmx_fit_rows(cvmx_t* h, int64_t row0, int64_t nrows, const void* X, int64_t ldx, const void* Y, int64_t ldy,
+                      const void* w, int32_t mem, int32_t gram);
+int32_t cvmx_fit_end(cvmx_t* h, int32_t col_shard, int32_t n_col_shards);
+/* Device addresses of Z (N x ld, handle dtype), w (N) and of the two moment rows (ld elements each). */
+int32_t cvmx_data_ptr(cvmx_t* h, void** Z, void** w, int64_t* ld);
+int32_t cvmx_moments_ptr(cvmx_t* h, void** sum_z, void** sumsq_z, int64_t* count);
+
 /* Device address and element count of the K x ld [XtWX | XtWY] totals (handle dtype), for an
  * external all-reduce (NCCL) between cvmx_fit on a row slab and cvmx_commit_totals. */
 int32_t cvmx_totals_ptr(cvmx_t* h, void** dev_ptr, int64_t* count, int64_t* ld);

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ctypes as C  # noqa: E402
 
 from cvmatrix_b200 import CVMatrix, Partitioner, _lib  # noqa: E402
-from cvmatrix_b200.distributed import ShardedFolds, fit_row_sharded  # noqa: E402
+from cvmatrix_b200.distributed import ShardedFolds, fit_row_sharded, fit_sharded_upload  # noqa: E402
 from cvmatrix_oracle import OracleCVMatrix, make_inputs, rel_fro  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,6 +45,19 @@ owned = torch.zeros(3, device="cuda")
 owned[out["fold_begin"]:out["fold_end"]] += 1
 dist.all_reduce(owned)
 assert bool((owned == 1).all())
+# sharded upload: every rank copies 1 / world of the rows over PCIe, slabs exchanged over NVLink, column-sharded sums
+m2 = CVMatrix(device=local)
+fit_sharded_upload(m2, X, Y, w, block_rows=7000)
+assert rel_fro(m2.XTX, orc.XTX) <= 1e-13 and rel_fro(m2.XTY, orc.XTY) <= 1e-13
+assert np.array_equal(m2.sum_X, orc.sum_X) and np.array_equal(m2.sum_sq_X, orc.sum_sq_X)
+assert np.array_equal(m2.sum_Y, orc.sum_Y) and np.array_equal(m2.sum_sq_Y, orc.sum_sq_Y)
+assert m2.sum_w == orc.sum_w and m2.num_nonzero_w == orc.nnz_w
+val = part.get_validation_indices(1)
+(XTX, XTY), stats = m2.training_XTX_XTY(val)
+r = orc.fold(val)
+assert rel_fro(XTX, r.XTX) <= 1e-12 and rel_fro(XTY, r.XTY) <= 1e-12
+for s, g in zip(stats, (r.X_mean, r.X_std, r.Y_mean, r.Y_std)):
+    assert np.array_equal(s, g)
 dist.barrier()
 if rank == 0:
     print("DIST_OK", world)
