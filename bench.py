@@ -268,7 +268,7 @@ def main():
 
     def step():
         if row_sharded:
-            # few large folds: rows of every fold split across ranks, 2 NCCL all-reduces, owners finish their folds
+            # few large folds: rows of every fold split across ranks, 1 NCCL all-reduce, owners finish their folds
             sf.training_batch(0, P, out=outs, row_sharded=True)
             return
         for c0 in range(f0, f1, chunk):
@@ -336,9 +336,18 @@ def main():
     # ---- end to end through the public API, host buffers in, host arrays out ------------------------------
     e2e = None
     if not args.no_e2e:
-        _lib.check(lib.cvmx_set_stream(h, None), h)
+        from cvmatrix_b200.distributed import fit_sharded_upload
+
+        if world == 1:
+            _lib.check(lib.cvmx_set_stream(h, None), h)
         e2e_steps = args.steps if cfg["P"] <= 1000 else max(1, min(args.steps, 2))
         out_bytes = 0
+        host_out = None
+        if row_sharded and world > 1:   # pinned host buffers for the folds this rank owns
+            o0, o1 = sharding.fold_block(rank, world, 0, P)
+            n_own = max(o1 - o0, 1)
+            host_out = {k: torch.empty((n_own,) + tuple(outs[k].shape[1:]), dtype=outs[k].dtype, pin_memory=True)
+                        for k in ("XTX", "XTY", "stats", "scal", "status")}
 
         parts = {"partitioner_ms": 0.0, "fit_ms": 0.0, "set_folds_ms": 0.0, "folds_ms": 0.0}
 
@@ -347,14 +356,27 @@ def main():
             t0 = time.perf_counter()
             p2 = Partitioner(folds)
             t1 = time.perf_counter()
-            m.fit(X, Y, w)
+            if world > 1:
+                # every rank uploads 1 / world of the rows over its own PCIe link; slabs are exchanged over NVLink
+                fit_sharded_upload(m, X, Y, w)
+            else:
+                m.fit(X, Y, w)
             t2 = time.perf_counter()
             m.set_folds(p2)
             t3 = time.perf_counter()
             out_bytes = 0
-            for c0 in range(f0, f1, chunk):
-                r = m.training_batch(c0, min(f1, c0 + chunk), out="numpy")
-                out_bytes += r["XTX"].nbytes + r["XTY"].nbytes + 2 * r["X_mean"].nbytes + 2 * r["Y_mean"].nbytes
+            if row_sharded and world > 1:
+                res = sf.training_batch(0, P, out=outs, row_sharded=True)
+                n = res["fold_end"] - res["fold_begin"]
+                for k, hbuf in host_out.items():
+                    if n > 0:
+                        hbuf[:n].copy_(outs[k][:n], non_blocking=True)
+                        out_bytes += hbuf[:n].numel() * hbuf.element_size()
+                torch.cuda.synchronize()
+            else:
+                for c0 in range(f0, f1, chunk):
+                    r = m.training_batch(c0, min(f1, c0 + chunk), out="numpy")
+                    out_bytes += r["XTX"].nbytes + r["XTY"].nbytes + 2 * r["X_mean"].nbytes + 2 * r["Y_mean"].nbytes
             t4 = time.perf_counter()
             for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 parts[k] += v * 1e3
@@ -369,13 +391,17 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        h2d = int(X.nbytes + Y.nbytes + w.nbytes) // world + int(part.indices.nbytes + part.offsets.nbytes)
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": P / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + w.nbytes + part.indices.nbytes + part.offsets.nbytes),
+            t = torch.tensor([dt, float(out_bytes)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+            dt, out_bytes = float(t[0].item()), int(t[1].item())
+            h2d *= world
+        e2e = {"value": P / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "includes": "Partitioner + fit (H2D from pinned host memory) + set_folds + all folds + D2H of every output",
+               "includes": ("Partitioner + fit (H2D from pinned host memory" + (f": 1/{world} of the rows per rank, slabs exchanged over NVLink" if world > 1 else "")
+                            + ") + set_folds + all folds + D2H of every output"),
                "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
 
     # ---- CPU baseline: numpy restatement of the reference on this box's host cores (rank 0, N = 1 only) ----
@@ -406,7 +432,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": (f"rows of each fold sharded x{world} + 2 NCCL all-reduces" if row_sharded else f"fold-sharded x{world}"),
+            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": (f"rows of each fold sharded x{world} + 1 NCCL all-reduce" if row_sharded else f"fold-sharded x{world}"),
                        "l2_policy": "inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8 else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2",
                        "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

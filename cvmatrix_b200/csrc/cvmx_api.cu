@@ -79,7 +79,6 @@ struct cvmx_handle {
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
   DevBuf scan_seg, scan_ok, scan_list, scan_cnt;
-  bool attr_scan = false;
   int64_t scan_launches = 0;
   int64_t launches = 0;
   // optional per-kernel timing (cvmx_profile_*): event pairs recorded on the handle stream
@@ -343,15 +342,14 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
         CU(h, h->scan_cnt.reserve((size_t)ny * 2 * mp.ld * sizeof(int)));
         sp.seg = h->scan_seg.as<double>(); sp.ok = h->scan_ok.as<int>();
         sp.slow_list = h->scan_list.as<int>(); sp.slow_cnt = h->scan_cnt.as<int>();
-        if (!h->attr_scan) {
-          CU(h, cudaFuncSetAttribute(k_scan_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_CHAIN_SMEM));
-          h->attr_scan = true;
-        }
-        const dim3 gseg((unsigned)mine, (unsigned)((max_segs + SCAN_WARPS - 1) / SCAN_WARPS), ny);
+        // (measured: capping the streaming grids to a few SMs' worth of CTAs and fatter chain CTAs while a Gram kernel
+        // owns the GPU does not change the step time - the passes cost the same SM time either way)
+        const int64_t quads = (max_segs + SCAN_WARPS - 1) / SCAN_WARPS;
+        const dim3 gseg((unsigned)mine, (unsigned)quads, ny);
         k_scan_segsums<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
         k_scan_prefix<<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp);
         k_scan_delta<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
-        k_scan_chain<<<dim3((unsigned)(mine * (SCAN_COLS / SCAN_CHAIN_COLS)), ny), SCAN_CHAIN_THREADS, SCAN_CHAIN_SMEM, h->stream>>>(sp);
+        k_scan_chain<2><<<dim3((unsigned)(mine * (SCAN_COLS / 2)), ny), 64 * 2, scan_chain_smem<2>(), h->stream>>>(sp);
         h->launches += 4; h->scan_launches += 1;
         q.scan_ok = sp.ok; q.scan_groups = sp.groups_total;
       }
@@ -954,7 +952,8 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
-  k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  k_partial_sum<<<dim3((unsigned)(GACC * GTHREADS / 512), (unsigned)ntiles, (unsigned)Pn), 256, 0, h->stream>>>(
+      h->partials.as<double>(), h->units.as<GramUnit>(), h->fold_units.as<int32_t>(), ntiles, out);
   h->launches++;
   prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
   CU(h, cudaGetLastError());

@@ -465,6 +465,32 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
   gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, tl.x, tl.y);
 }
 
+// Row-split partials of (fold, tile) summed in split order into raw fragment buffers, element-parallel: the sharded
+// (multi-GPU) Gram phase has only folds x tiles reduce CTAs, too few to pull the partials at HBM rate.
+//   out[fold][tile][e] = sum_s partials[part_base(fold) + s][tile][e],  e < GACC * GTHREADS
+__global__ void __launch_bounds__(256) k_partial_sum(const double* __restrict__ partials, const GramUnit* __restrict__ units,
+                                                     const int32_t* __restrict__ fold_units, int ntiles, double* __restrict__ out) {
+  const int fold = blockIdx.z, tile = blockIdx.y;
+  const GramUnit unit = units[fold_units[fold]];
+  const size_t tile_elems = (size_t)GACC * GTHREADS, split_stride = (size_t)ntiles * tile_elems;
+  const size_t e = ((size_t)blockIdx.x * 256 + threadIdx.x) * 2;
+  const double* src = partials + ((size_t)unit.part_base * ntiles + tile) * tile_elems + e;
+  double2 acc = *reinterpret_cast<const double2*>(src);
+  int s = 1;
+  for (; s + 4 <= unit.nsplit; s += 4) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const double2*>(src + (size_t)(s + u) * split_stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+  }
+  for (; s < unit.nsplit; ++s) {
+    const double2 v = *reinterpret_cast<const double2*>(src + (size_t)s * split_stride);
+    acc.x += v.x; acc.y += v.y;
+  }
+  *reinterpret_cast<double2*>(out + ((size_t)unit.fold * ntiles + tile) * tile_elems + e) = acc;
+}
+
 // CSR index normalisation: numpy wrap-around for negative indices, error flag for out-of-range ones.
 __global__ void k_normalize_indices(int64_t* __restrict__ idx, int64_t n, int64_t N, int32_t* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

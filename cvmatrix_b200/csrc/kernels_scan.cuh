@@ -98,25 +98,27 @@ __global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_segsums(ScanParams sp)
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
   const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
-  const int64_t s = (int64_t)blockIdx.y * SCAN_WARPS + warp;
-  const int64_t r0 = s * sp.L;
   if (blockIdx.y == 0 && threadIdx.x == 0) sp.ok[f * sp.groups_total + p.grp0 + blockIdx.x * p.grp_stride] = 1;   // pass 2 clears it
-  if (r0 >= n) return;
-  const int cnt = (int)min((int64_t)sp.L, n - r0);
-  double S = 0.0, A = 0.0, Q = 0.0;
-  unsigned negq = 0;
-  scan_rows(p, idx, r0, cnt, lane, p.Z + c, [&](double t, double q) {
-    S = __dadd_rn(S, t);
-    A = __dadd_rn(A, fabs(t));
-    Q = __dadd_rn(Q, fabs(q));
-    negq |= (unsigned)(__double2hiint(q) & 0x80000000);
-  });
-  // q = rn(rn(w z) z) is non-negative unless a weight is negative (fit rejects those) - then the squares chain is
-  // never fast (NaN magnitude)
-  scan_plane(sp, f, 0, 0, c)[s] = S;
-  scan_plane(sp, f, 0, 1, c)[s] = A;
-  scan_plane(sp, f, 1, 0, c)[s] = Q;
-  scan_plane(sp, f, 1, 1, c)[s] = negq ? __longlong_as_double(0x7ff8000000000000LL) : Q;
+  // gridDim.y may be smaller than the number of segment quads (a grid capped to a few SMs' worth of CTAs while a
+  // Gram kernel owns the rest of the GPU): CTAs stride over the quads
+  for (int64_t s = (int64_t)blockIdx.y * SCAN_WARPS + warp; s * sp.L < n; s += (int64_t)gridDim.y * SCAN_WARPS) {
+    const int64_t r0 = s * sp.L;
+    const int cnt = (int)min((int64_t)sp.L, n - r0);
+    double S = 0.0, A = 0.0, Q = 0.0;
+    unsigned negq = 0;
+    scan_rows(p, idx, r0, cnt, lane, p.Z + c, [&](double t, double q) {
+      S = __dadd_rn(S, t);
+      A = __dadd_rn(A, fabs(t));
+      Q = __dadd_rn(Q, fabs(q));
+      negq |= (unsigned)(__double2hiint(q) & 0x80000000);
+    });
+    // q = rn(rn(w z) z) is non-negative unless a weight is negative (fit rejects those) - then the squares chain is
+    // never fast (NaN magnitude)
+    scan_plane(sp, f, 0, 0, c)[s] = S;
+    scan_plane(sp, f, 0, 1, c)[s] = A;
+    scan_plane(sp, f, 1, 0, c)[s] = Q;
+    scan_plane(sp, f, 1, 1, c)[s] = negq ? __longlong_as_double(0x7ff8000000000000LL) : Q;
+  }
 }
 
 // ---- pass 2 -----------------------------------------------------------------------------------------------------
@@ -225,32 +227,32 @@ __global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_delta(ScanParams sp) {
   const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
   const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
   const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
-  const int64_t s = (int64_t)blockIdx.y * SCAN_WARPS + warp;
-  const int64_t r0 = s * sp.L;
-  if (r0 >= n) return;
-  const int cnt = (int)min((int64_t)sp.L, n - r0);
-  double *o00 = scan_plane(sp, f, 0, 0, c) + s, *o01 = scan_plane(sp, f, 0, 1, c) + s;
-  double *o10 = scan_plane(sp, f, 1, 0, c) + s, *o11 = scan_plane(sp, f, 1, 1, c) + s;
-  const double Bs = *o00, Bq = *o10;
-  const long long bs = __double_as_longlong(Bs), bq = __double_as_longlong(Bq);
-  if (__all_sync(0xffffffffu, bs == 0 && bq == 0)) return;
-  // identity segments (B = -0) use the same start for both parities; otherwise the odd proxy is B + u
-  const bool ids = bs == (long long)0x8000000000000000ULL, idq = bq == (long long)0x8000000000000000ULL;
-  const double Bs1 = ids ? Bs : __longlong_as_double(bs | 1), Bq1 = idq ? Bq : __longlong_as_double(bq | 1);
-  double c0 = Bs, c1 = Bs1, e0 = Bq, e1 = Bq1;
-  scan_rows(p, idx, r0, cnt, lane, p.Z + c, [&](double t, double q) {
-    c0 = __dadd_rn(c0, t);
-    c1 = __dadd_rn(c1, t);
-    e0 = __dadd_rn(e0, q);
-    e1 = __dadd_rn(e1, q);
-  });
-  if (bs != 0) {
-    *o00 = ids ? c0 : __dsub_rn(c0, Bs);
-    *o01 = ids ? c1 : __dsub_rn(c1, Bs1);
-  }
-  if (bq != 0) {
-    *o10 = idq ? e0 : __dsub_rn(e0, Bq);
-    *o11 = idq ? e1 : __dsub_rn(e1, Bq1);
+  for (int64_t s = (int64_t)blockIdx.y * SCAN_WARPS + warp; s * sp.L < n; s += (int64_t)gridDim.y * SCAN_WARPS) {
+    const int64_t r0 = s * sp.L;
+    const int cnt = (int)min((int64_t)sp.L, n - r0);
+    double *o00 = scan_plane(sp, f, 0, 0, c) + s, *o01 = scan_plane(sp, f, 0, 1, c) + s;
+    double *o10 = scan_plane(sp, f, 1, 0, c) + s, *o11 = scan_plane(sp, f, 1, 1, c) + s;
+    const double Bs = *o00, Bq = *o10;
+    const long long bs = __double_as_longlong(Bs), bq = __double_as_longlong(Bq);
+    if (__all_sync(0xffffffffu, bs == 0 && bq == 0)) continue;
+    // identity segments (B = -0) use the same start for both parities; otherwise the odd proxy is B + u
+    const bool ids = bs == (long long)0x8000000000000000ULL, idq = bq == (long long)0x8000000000000000ULL;
+    const double Bs1 = ids ? Bs : __longlong_as_double(bs | 1), Bq1 = idq ? Bq : __longlong_as_double(bq | 1);
+    double c0 = Bs, c1 = Bs1, e0 = Bq, e1 = Bq1;
+    scan_rows(p, idx, r0, cnt, lane, p.Z + c, [&](double t, double q) {
+      c0 = __dadd_rn(c0, t);
+      c1 = __dadd_rn(c1, t);
+      e0 = __dadd_rn(e0, q);
+      e1 = __dadd_rn(e1, q);
+    });
+    if (bs != 0) {
+      *o00 = ids ? c0 : __dsub_rn(c0, Bs);
+      *o01 = ids ? c1 : __dsub_rn(c1, Bs1);
+    }
+    if (bq != 0) {
+      *o10 = idq ? e0 : __dsub_rn(e0, Bq);
+      *o11 = idq ? e1 : __dsub_rn(e1, Bq1);
+    }
   }
 }
 
@@ -259,13 +261,14 @@ __global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_delta(ScanParams sp) {
 // staged 32 segments at a time through shared memory, the next 32 in flight).  Slow segments come from the list of
 // pass 2 and run a three-stage software pipeline: row indices of slow segment k + 2 and the gathered values of k + 1
 // are in flight while the 32 lanes' products of segment k are added row by row, in the reference order.
-constexpr int SCAN_CHAIN_COLS = 2;                                    // columns per CTA (x 2 chains = 4 warps: one per SM sub-partition)
-constexpr int SCAN_CHAIN_THREADS = 64 * SCAN_CHAIN_COLS;
+// Columns per CTA (x 2 chains = warps): 2 puts one warp on each SM sub-partition, so the dependent adds do not
+// queue behind each other on the FP64 pipe (8 columns per CTA: 134 us instead of 90 us at cfg 2 / 8 shards).
 constexpr int SCAN_NB = SCAN_L / 32;
-constexpr size_t SCAN_CHAIN_SMEM = (size_t)2 * SCAN_CHAIN_COLS * (SCAN_L + 64) * sizeof(double);
+template <int COLS> constexpr size_t scan_chain_smem() { return (size_t)2 * COLS * (SCAN_L + 64) * sizeof(double); }
 static_assert(SCAN_L % 32 == 0, "segments are gathered 32 rows at a time");
 
-__global__ void __launch_bounds__(SCAN_CHAIN_THREADS) k_scan_chain(ScanParams sp) {
+template <int SCAN_CHAIN_COLS>
+__global__ void __launch_bounds__(64 * SCAN_CHAIN_COLS) k_scan_chain(ScanParams sp) {
   extern __shared__ __align__(16) unsigned char scan_smem[];
   __shared__ double sres[SCAN_CHAIN_COLS];
   const MomentParams<double>& p = sp.p;

@@ -29,7 +29,7 @@ class ShardedFolds:
     ``training_batch`` returns device tensors for the folds THIS rank owns (a contiguous block, see
     ``sharding.fold_block``): dict(fold_begin, fold_end, XTX, XTY, stats, scal, status).  Many folds: each rank
     simply evaluates its block.  Few folds: every rank computes the raw Gram of its row shard of every fold and the
-    moment chains of its column groups; two all-reduces assemble them; each rank then finishes its own folds.
+    moment sums of its column groups; one all-reduce assembles both; each rank then finishes its own folds.
     """
 
     def __init__(self, cvm: CVMatrix, group=None):
@@ -76,15 +76,18 @@ class ShardedFolds:
         shards = self.emulate_shards or self.world
         _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, shards, C.byref(sp), C.byref(sc)), h)
         n = lib.cvmx_sharded_gram_count(h, f0, f1, 3)
-        if self._gram is None or self._gram.numel() < n:
-            self._gram = t.empty((n,), dtype=t.float64, device=self.dev)
+        # one buffer for both reductions: [raw Grams | statistics rows widened to float64] -> ONE all-reduce
+        if self._gram is None or self._gram.numel() < n + sc.value:
+            self._gram = t.empty((n + sc.value,), dtype=t.float64, device=self.dev)
         gram = self._gram[:n]
         _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, shards, vp(gram)), h)
         _lib.check(lib.cvmx_sharded_stats_wait(h), h)   # the chains ran on a side stream beside the Gram kernel
         if self.world > 1:
             stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8" if self.tdt == t.float64 else "<f4"), device=self.dev)
-            self.dist.all_reduce(stats, group=self.group)
-            self.dist.all_reduce(gram, group=self.group)
+            tail = self._gram[n:n + sc.value]
+            tail.copy_(stats)
+            self.dist.all_reduce(self._gram[:n + sc.value], group=self.group)
+            stats.copy_(tail)   # foreign entries were zero: the sum is exact in either dtype
         _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
                                            vp(out["scal"]), vp(out["status"])), h)
         return dict(out, fold_begin=o0, fold_end=o1)
