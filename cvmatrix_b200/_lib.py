@@ -34,6 +34,8 @@ SIGNATURES = {
     "cvmx_commit_totals": (_i32, [_vp]),
     "cvmx_get_totals": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cvmx_set_folds": (_i32, [_vp, _vp, _vp, _i64, _i32]),
+    "cvmx_fit_folds": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _i64, _i32]),
+    "cvmx_folds_are_cached": (_i32, [_vp]),
     "cvmx_training_batch": (_i32, [_vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_training_indices": (_i32, [_vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "cvmx_sharded_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_i64)]),

@@ -74,6 +74,10 @@ struct cvmx_handle {
   bool attr_gram = false, attr_mom = false;
   // binade scan of the moment chains (kernels_scan.cuh): 0 off, 1 when the chains are the critical path, 2 always
   int scan_mode = 1;
+  // fused fit + folds (cvmx_fit_folds): raw float64 Gram of every fold of a true partition, [P][ntiles][GACC][GTHREADS],
+  // valid while csr_version == fold_gram_version; cvmx_training_batch then only runs statistics + epilogue
+  DevBuf fold_gram;
+  int64_t fold_gram_version = -1;
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
   bool filling = false;
   int64_t fill_units_cap = 0, fill_calls = 0;
@@ -448,9 +452,16 @@ __global__ void k_pack_scalars(const FoldScalars* __restrict__ fs, int64_t n, T*
 }
 
 // ---- fit -------------------------------------------------------------------------------------------
+int32_t upload_csr(cvmx_t* h, DevBuf& doff, DevBuf& didx, const int64_t* offsets, const int64_t* indices, int64_t P,
+                   int64_t nidx, int32_t mem);
+
+// Host CSR of a TRUE partition of the rows (every row in exactly one fold, indices ascending inside a fold): then
+// XtWX = sum over folds of the fold Grams, so fit can contract every row once, per fold, and keep the fold Grams.
+struct FoldFuse { const int64_t* off; const int64_t* idx; int64_t P; };
+
 template <typename T>
 int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M, int64_t ldy,
-                 const void* w, int32_t mem, int64_t g0, int64_t g1) {
+                 const void* w, int32_t mem, int64_t g0, int64_t g1, const FoldFuse* ff = nullptr) {
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
   h->fitted = false;
@@ -538,38 +549,98 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
     const int64_t unit_rows = 2816;          // ~176 stages per Gram CTA
     // units of every chunk (clipped to the Gram slab [g0, g1)), numbered globally: one fold with `total` splits
     std::vector<int64_t> chunk_unit0;
-    for (int64_t r0 = 0; r0 < N; r0 += chunk_rows) {
-      chunk_unit0.push_back((int64_t)pl.units.size());
-      const int64_t a0 = std::max(r0, g0), a1 = std::min(std::min(r0 + chunk_rows, N), g1);
-      for (int64_t u0 = a0; u0 < a1; u0 += unit_rows) {
-        GramUnit u;
-        u.row_begin = u0; u.row_end = std::min(a1, u0 + unit_rows);
-        u.fold = 0; u.split = (int32_t)pl.units.size(); u.nsplit = 0; u.part_base = 0;
-        pl.units.push_back(u);
+    // fused fit + folds: the rows of a chunk are contracted fold by fold (CSR position ranges, gathered through the
+    // device CSR); partial slots are numbered fold-major so that one pass sums them per fold
+    bool fused = ff != nullptr && g0 == 0 && g1 == N && ff->P > 0;
+    std::vector<int64_t> fold_base, fold_n;
+    if (fused) {
+      const int64_t P = ff->P;
+      struct Piece { int64_t lo, hi; int32_t fold; };
+      std::vector<std::vector<Piece>> per_chunk;
+      fold_n.assign(P, 0);
+      for (int64_t r0 = 0; r0 < N; r0 += chunk_rows) {
+        const int64_t r1 = std::min(r0 + chunk_rows, N);
+        per_chunk.emplace_back();
+        for (int64_t f = 0; f < P; ++f) {
+          const int64_t* b = ff->idx + ff->off[f];
+          const int64_t* e = ff->idx + ff->off[f + 1];
+          const int64_t lo = std::lower_bound(b, e, r0) - ff->idx, hi = std::lower_bound(b, e, r1) - ff->idx;
+          const int64_t n = hi - lo;
+          if (n <= 0) continue;
+          const int64_t ns = (n + unit_rows - 1) / unit_rows, per = round_up((n + ns - 1) / ns, GBK);
+          for (int64_t s2 = 0; s2 < ns; ++s2) {
+            const int64_t a = lo + std::min(n, s2 * per), z = lo + std::min(n, (s2 + 1) * per);
+            if (z > a) { per_chunk.back().push_back({a, z, (int32_t)f}); fold_n[f]++; }
+          }
+        }
+      }
+      int64_t tot = 0;
+      fold_base.assign(P, 0);
+      for (int64_t f = 0; f < P; ++f) { fold_base[f] = tot; tot += fold_n[f]; if (fold_n[f] == 0) fused = false; }
+      if ((size_t)(tot + P) * ntiles * GACC * GTHREADS * sizeof(double) > ((size_t)2 << 30)) fused = false;   // many small folds: not worth it
+      if (fused) {
+        std::vector<int64_t> next(fold_base);
+        for (auto& pieces : per_chunk) {
+          chunk_unit0.push_back((int64_t)pl.units.size());
+          for (auto& pc : pieces) {
+            GramUnit u;
+            u.row_begin = pc.lo; u.row_end = pc.hi; u.fold = pc.fold; u.split = (int32_t)next[pc.fold]++; u.nsplit = 0; u.part_base = 0;
+            pl.units.push_back(u);
+          }
+        }
+      }
+    }
+    if (fused) {
+      int32_t rcu = upload_csr(h, h->d_off, h->d_idx, ff->off, ff->idx, ff->P, ff->off[ff->P], CVMX_HOST);
+      if (rcu) { h->stream = main_stream; return rcu; }
+    } else {
+      for (int64_t r0 = 0; r0 < N; r0 += chunk_rows) {
+        chunk_unit0.push_back((int64_t)pl.units.size());
+        const int64_t a0 = std::max(r0, g0), a1 = std::min(std::min(r0 + chunk_rows, N), g1);
+        for (int64_t u0 = a0; u0 < a1; u0 += unit_rows) {
+          GramUnit u;
+          u.row_begin = u0; u.row_end = std::min(a1, u0 + unit_rows);
+          u.fold = 0; u.split = (int32_t)pl.units.size(); u.nsplit = 0; u.part_base = 0;
+          pl.units.push_back(u);
+        }
       }
     }
     chunk_unit0.push_back((int64_t)pl.units.size());
     // wide K: one partial per 2816 rows x ntiles tiles would not fit (K = 5000: 107 MB per unit) - then the Gram pass
     // runs after the upload with longer units instead of chunk by chunk
     const bool pipeline_gram = (size_t)pl.units.size() * ntiles * GACC * GTHREADS * sizeof(double) <= ((size_t)2 << 30);
-    if (!pipeline_gram) { pl.units.clear(); for (auto& u0 : chunk_unit0) u0 = 0; }
+    if (!pipeline_gram) { pl.units.clear(); for (auto& u0 : chunk_unit0) u0 = 0; fused = false; }
     const int32_t total = (int32_t)pl.units.size();
     for (auto& u : pl.units) u.nsplit = total;                // force_partials: always the partial + reduce path
     pl.fold_units.assign(1, 0);
     pl.split_folds.assign(1, 0);
+    std::vector<int32_t> h_fold_units(1, 0);
+    if (fused) {
+      // virtual units: [total + f] = fold f's slots; [total + P] = the P per-fold sums (-> totals)
+      const int64_t P = ff->P;
+      h_fold_units.assign(P + 1, 0);
+      for (int64_t f = 0; f <= P; ++f) {
+        GramUnit v;
+        v.row_begin = v.row_end = 0; v.split = 0;
+        v.fold = f < P ? (int32_t)f : 0; v.part_base = f < P ? (int32_t)fold_base[f] : 0; v.nsplit = f < P ? (int32_t)fold_n[f] : (int32_t)P;
+        h_fold_units[f] = (int32_t)pl.units.size();
+        pl.units.push_back(v);
+      }
+      CU(h, h->fold_gram.reserve((size_t)P * ntiles * GACC * GTHREADS * sizeof(double)));
+    }
     GramParams<T> gp;
-    gp.Z = Z; gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
+    gp.Z = Z; gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = fused ? h->d_idx.as<int64_t>() : nullptr;
     gp.ntiles = ntiles; gp.raw_out = nullptr; gp.force_partials = 1; gp.epi = epi;
     const size_t smem = gram_smem_bytes<T>();
     if (total > 0) {
       CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
       CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
-      CU(h, h->fold_units.reserve(sizeof(int32_t)));
+      CU(h, h->fold_units.reserve(h_fold_units.size() * sizeof(int32_t)));
       CU(h, h->split_folds.reserve(sizeof(int32_t)));
       CU(h, h->partials.reserve((size_t)total * ntiles * GACC * GTHREADS * sizeof(double)));
       CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
       CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-      CU(h, cudaMemsetAsync(h->fold_units.p, 0, sizeof(int32_t), h->stream));
+      CU(h, cudaMemcpyAsync(h->fold_units.p, h_fold_units.data(), h_fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
       CU(h, cudaMemsetAsync(h->split_folds.p, 0, sizeof(int32_t), h->stream));
       if (!h->attr_gram) {
         CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -613,11 +684,26 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       }
     }
     CU(h, cudaGetLastError());
-    if (total > 0) {
+    if (total > 0 && fused) {
+      // per-fold sums of the partial slots (kept: cvmx_training_batch finishes the folds from them), then totals =
+      // sum over folds
+      gp.units = h->units.as<GramUnit>();
+      k_partial_sum<<<dim3((unsigned)(GACC * GTHREADS / 512), (unsigned)ntiles, (unsigned)ff->P), 256, 0, h->stream>>>(
+          h->partials.as<double>(), h->units.as<GramUnit>(), h->fold_units.as<int32_t>(), ntiles, h->fold_gram.as<double>());
+      gp.partials = h->fold_gram.as<double>();
+      k_gram_reduce<T><<<dim3(ntiles, 1), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>() + ff->P, h->split_folds.as<int32_t>());
+      h->launches += 2;
+      CU(h, cudaGetLastError());
+    } else if (total > 0) {
       gp.units = h->units.as<GramUnit>();
       k_gram_reduce<T><<<dim3(ntiles, 1), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
       h->launches++;
       CU(h, cudaGetLastError());
+    }
+    if (fused && total > 0) {
+      h->P = ff->P;
+      h->h_off.assign(ff->off, ff->off + ff->P + 1);
+      h->fold_gram_version = h->csr_version;
     }
     CU(h, cudaEventRecord(h->ev_join, stats_stream));
     if (!pipeline_gram && g1 > g0) {
@@ -815,6 +901,9 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
   return CVMX_OK;
 }
 
+template <typename T>
+int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy);
+
 // ---- folds -----------------------------------------------------------------------------------------
 // Runs folds [f0, f1) of the CSR (d_off/d_idx on device, off on host) and leaves results in device
 // buffers: dxx [P'][K][K], dxy [P'][K][M] (either may be null per `want`), stats scratch, fscal scratch.
@@ -824,6 +913,17 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   const int64_t Pn = f1 - f0;
   if (Pn <= 0) return CVMX_OK;
   const int64_t ld = h->ld, K = h->K, M = h->M;
+  if (cacheable && h->fold_gram_version == h->csr_version && (want & 3u) == (CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0u))) {
+    // cvmx_fit_folds kept the raw Gram of every fold: only the statistics and the epilogue are left
+    int64_t max_rows = 0;
+    for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, off[f + 1] - off[f]);
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, max_rows, 0, 1, 0.0);
+    if (rc) return rc;
+    std::vector<int2> tiles;
+    plan_tiles(h, want, tiles);
+    const double* gram = h->fold_gram.as<double>() + (size_t)f0 * tiles.size() * GACC * GTHREADS;
+    return sharded_finish<T>(h, f0, f0, f1, want, gram, dxx, dxy);
+  }
   Plan local;
   Plan& pl = cacheable ? h->plan : local;
   const bool hit = cacheable && pl.fold_begin == f0 && pl.fold_end == f1 && pl.want == want && pl.csr_version == h->csr_version;
@@ -1146,7 +1246,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
-                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage})
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
@@ -1285,6 +1385,38 @@ int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices
   h->P = P;
   return CVMX_OK;
 }
+
+
+int32_t cvmx_fit_folds(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M, int64_t ldy,
+                       const void* w, int32_t mem, const int64_t* offsets, const int64_t* indices, int64_t P, int32_t is_partition) {
+  if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  if (!X || N < 0 || K <= 0 || ldx < K || M < 0 || (M > 0 && (!Y || ldy < M)) || !offsets || P < 0 || (P > 0 && offsets[P] > 0 && !indices))
+    return fail(h, CVMX_ERR_INVALID, "cvmx_fit_folds: bad arguments");
+  CU(h, cudaSetDevice(h->device));
+  if (!Y) M = 0;
+  if (offsets[0] != 0) return fail(h, CVMX_ERR_INVALID, "offsets[0] must be 0");
+  for (int64_t f = 0; f < P; ++f)
+    if (offsets[f + 1] < offsets[f]) return fail(h, CVMX_ERR_INVALID, "offsets must be non-decreasing");
+  // the fusion needs a true partition with ascending indices inside every fold
+  bool part = P > 0 && offsets[P] == N;
+  if (part && !is_partition) {
+    std::vector<unsigned char> seen((size_t)N, 0);
+    for (int64_t f = 0; f < P && part; ++f)
+      for (int64_t i = offsets[f]; i < offsets[f + 1]; ++i) {
+        const int64_t r = indices[i];
+        if (r < 0 || r >= N || seen[r] || (i > offsets[f] && indices[i - 1] >= r)) { part = false; break; }
+        seen[r] = 1;
+      }
+  }
+  FoldFuse ff{offsets, indices, P};
+  int32_t rc = h->dtype == CVMX_F64 ? fit_impl<double>(h, X, N, K, ldx, Y, M, ldy, w, mem, 0, N, part ? &ff : nullptr)
+                                    : fit_impl<float>(h, X, N, K, ldx, Y, M, ldy, w, mem, 0, N, part ? &ff : nullptr);
+  if (rc) return rc;
+  if (h->fold_gram_version == h->csr_version) return CVMX_OK;   // fused: the CSR is already resident
+  return cvmx_set_folds(h, offsets, indices, P, CVMX_HOST);
+}
+
+int32_t cvmx_folds_are_cached(const cvmx_t* h) { return h && h->fitted && h->fold_gram_version == h->csr_version ? 1 : 0; }
 
 int32_t cvmx_training_batch(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, void* oxx, void* oxy, void* ostats, void* oscal,
                             int32_t* ostatus, int32_t mem) {

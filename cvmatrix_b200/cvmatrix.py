@@ -170,8 +170,12 @@ class CVMatrix:
         return a, max(a.shape[1], 1)
 
     def fit(self, X: npt.ArrayLike, Y: Optional[npt.ArrayLike] = None, weights: Optional[npt.ArrayLike] = None,
-            _gram_rows: Optional[Tuple[int, int]] = None) -> None:
-        """cvmatrix/cvmatrix.py:207-328.  Uploads X, Y, weights and computes the dataset-wide totals on the GPU."""
+            _gram_rows: Optional[Tuple[int, int]] = None, folds: Optional[Partitioner] = None) -> None:
+        """cvmatrix/cvmatrix.py:207-328.  Uploads X, Y, weights and computes the dataset-wide totals on the GPU.
+
+        ``folds`` (extension): a ``Partitioner`` whose validation sets are uploaded in the same call
+        (= ``fit`` + ``set_folds``).  Its folds partition the rows, so every row is contracted once, per fold, behind
+        the upload, and ``training_batch`` afterwards only runs the statistics and the epilogue (cvmx_fit_folds)."""
         self._streamed = False
         self.X = self._init_mat(X)
         self.N, self.K = self.X.shape
@@ -192,8 +196,20 @@ class CVMatrix:
         Yd, ldy = self._rows(self.Y) if self.Y is not None else (None, 0)
         wd = np.ascontiguousarray(self.weights.reshape(-1)) if self.weights is not None else None
         g0, g1 = (0, self.N) if _gram_rows is None else _gram_rows
-        rc = self._lib.cvmx_fit(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST, g0, g1)
-        _lib.check(rc, self._h)
+        if folds is not None:
+            if _gram_rows is not None:
+                raise ValueError("folds= cannot be combined with a row-sharded Gram pass")
+            offsets, indices = folds.csr()
+            if indices.size != self.N:
+                raise ValueError("the Partitioner was built for a different number of rows")
+            rc = self._lib.cvmx_fit_folds(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST,
+                                          _ptr(offsets), _ptr(indices), offsets.size - 1, 1)
+            _lib.check(rc, self._h)
+            self._partitioner = folds
+            self._n_folds = offsets.size - 1
+        else:
+            rc = self._lib.cvmx_fit(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST, g0, g1)
+            _lib.check(rc, self._h)
         self._pull_totals()
 
     # ---- streaming / sharded fit (include/cvmx.h: cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end) -------------------
@@ -479,6 +495,11 @@ class CVMatrix:
         0 dependent-add chains only, 1 (default) the bit-identical binade scan when the chains are on the critical
         path, 2 the scan whenever a fold has >= 1024 rows."""
         _lib.check(self._lib.cvmx_set_scan_mode(self._h, int(mode)), self._h)
+
+    @property
+    def folds_cached(self) -> bool:
+        """True while the fold Grams kept by ``fit(..., folds=...)`` serve ``training_batch``."""
+        return bool(self._lib.cvmx_folds_are_cached(self._h))
 
     @property
     def scan_launch_count(self) -> int:

@@ -133,6 +133,21 @@ int32_t cvmx_get_totals(cvmx_t* h, void* XTX, void* XTY, void* sum_X, void* sum_
 int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P, int32_t mem);
 
 /*
+ * cvmx_fit + cvmx_set_folds in one call (host pointers).  When the folds are a TRUE partition of the rows (every row in
+ * exactly one fold, indices ascending inside a fold - what Partitioner produces, cvmatrix/partitioner.py:89-107) and
+ * the matrix takes the chunk-pipelined upload, XtWX = sum over folds of the fold Grams: every row is contracted ONCE,
+ * per fold, behind the host->device copy, the raw fold Grams are kept, and a later cvmx_training_batch(XTX|XTY) only
+ * runs the statistics and the centering / scaling epilogue (the reference evaluates 2 N K (K+M) flops in fit and the
+ * same again over the folds, cvmatrix/cvmatrix.py:1215-1217 and :1001).  Otherwise it behaves exactly like the two
+ * separate calls.  is_partition != 0 skips the O(N) verification (the caller vouches for it).
+ * cvmx_folds_are_cached: 1 while the kept fold Grams match the current CSR.
+ */
+int32_t cvmx_fit_folds(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, const void* Y, int64_t M, int64_t ldy,
+                       const void* w, int32_t mem, const int64_t* offsets, const int64_t* indices, int64_t P,
+                       int32_t is_partition);
+int32_t cvmx_folds_are_cached(const cvmx_t* h);
+
+/*
  * Batched replacement of _training_matrices / training_statistics for folds
  * [fold_begin, fold_end) of the CSR (cvmatrix/cvmatrix.py:754-896, 519-574; per fold:
  * _get_sum_w_train_and_num_nonzero_w_train :589-630, _compute_training_stats :632-752,
