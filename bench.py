@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-out", default="numpy", choices=["numpy", "pinned"],
+                    help="host destination of the e2e results: fresh numpy arrays (the reference's convention) or the reused page-locked pool")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", 0))
@@ -378,7 +380,7 @@ def main():
                 torch.cuda.synchronize()
             else:
                 for c0 in range(f0, f1, chunk):
-                    r = m.training_batch(c0, min(f1, c0 + chunk), out="numpy")
+                    r = m.training_batch(c0, min(f1, c0 + chunk), out=args.e2e_out)
                     out_bytes += r["XTX"].nbytes + r["XTY"].nbytes + 2 * r["X_mean"].nbytes + 2 * r["Y_mean"].nbytes
             t4 = time.perf_counter()
             for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
@@ -405,7 +407,7 @@ def main():
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
                "includes": ("Partitioner + fit (H2D from pinned host memory" + (f": 1/{world} of the rows per rank, slabs exchanged over NVLink" if world > 1 else "; fused with the fold Grams when the folds partition the rows")
                             + ") + set_folds + all folds + D2H of every output"),
-               "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
+               "host_outputs": args.e2e_out, "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
 
     # ---- CPU baseline: numpy restatement of the reference on this box's host cores (rank 0, N = 1 only) ----
     cpu = None

@@ -302,6 +302,14 @@ def test_torch_device_outputs():
     assert dev["XTX"].is_cuda and dev["XTX"].dtype == torch.float64
     assert np.array_equal(dev["XTX"].cpu().numpy(), host["XTX"]) and np.array_equal(dev["XTY"].cpu().numpy(), host["XTY"])
     assert np.array_equal(dev["X_std"].cpu().numpy(), host["X_std"])
+    # page-locked pool: same values, reused (overwritten) by the next out="pinned" call
+    pin = m.training_batch(out="pinned")
+    assert np.array_equal(pin["XTX"], host["XTX"]) and np.array_equal(pin["Y_mean"], host["Y_mean"])
+    assert np.array_equal(pin["status"], host["status"]) and np.array_equal(pin["sum_w_train"], host["sum_w_train"])
+    first = pin["XTX"][0].copy()
+    pin2 = m.training_batch(2, 5, out="pinned")
+    assert np.shares_memory(pin2["XTX"], pin["XTX"]) and np.array_equal(pin2["XTX"][0], host["XTX"][2])
+    assert not np.array_equal(pin["XTX"][0], first)
 
 
 @pytest.mark.parametrize("n_shards", [1, 3])
