@@ -325,6 +325,15 @@ def main():
         ach = bytes_per_step / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else None
         roof = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw if ach else None,
                 "peak_source": bw_src}
+    if roof["bound"] == "tensor" and ach:
+        # flops the kernel actually issues: tiles on / above the diagonal only, diagonal tiles at 3/4
+        TI, TJ = -(-K // 128), -(-(K + M) // 128)
+        issued_tiles = sum((0.75 if bj == bi else 1.0) for bi in range(TI) for bj in range(bi, TJ))
+        issued = 2.0 * n_val_total * 128 * 128 * issued_tiles
+        roof["issued_flops_per_step"] = issued
+        roof["issued_frac_of_peak"] = issued / (gram_ms * 1e-3) / 1e12 / peak_tf
+        roof["note"] = ("achieved / frac use the FULL flop count 2 N_val K (K+M) of SURVEY.md 8(d); XTX is symmetric, so only "
+                        "upper-triangular tiles are computed and frac can exceed 1 - issued_frac_of_peak is the DMMA pipe's own load")
     roof.update({"kernel": "k_gram<double>", "traffic": None, "kernel_ms_per_step": gram_ms, "kernel_launches_per_step": gram_launches,
                  "stats_ms_per_step": prof_ms[0] / max(1, args.steps), "reduce_ms_per_step": prof_ms[2] / max(1, args.steps),
                  "algorithmic_flops_per_step": flops_per_step, "algorithmic_bytes_per_step": bytes_per_step,

@@ -76,7 +76,7 @@ struct cvmx_handle {
   int scan_mode = 1;
   // fused fit + folds (cvmx_fit_folds): raw float64 Gram of every fold of a true partition, [P][ntiles][GACC][GTHREADS],
   // valid while csr_version == fold_gram_version; cvmx_training_batch then only runs statistics + epilogue
-  DevBuf fold_gram;
+  DevBuf fold_gram, fold_raw, chunk_ranges;   // fold_raw: [P][2][ld] raw column sums of every fold, same validity
   int64_t fold_gram_version = -1;
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
   bool filling = false;
@@ -309,7 +309,7 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
   // through to k_moments_pipe below.
   bool scan = false;
   const int64_t max_segs = round_up((max_rows + SCAN_L - 1) / SCAN_L, SCAN_PER_LANE);
-  if (std::is_same<T, double>::value && pipe && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
+  if (std::is_same<T, double>::value && pipe && !mp.ranges && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
     const size_t seg_bytes = (size_t)std::min<int64_t>(65535, nfolds) * max_segs * 4 * mp.ld * sizeof(double);
     const int64_t groups0 = mp.ld / MOM_COLS;
     const int64_t mine0 = groups0 > col_shard ? (groups0 - col_shard + n_col_shards - 1) / n_col_shards : 0;
@@ -324,11 +324,12 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
   for (int64_t f0 = 0; f0 < nfolds; f0 += 65535) {
     const unsigned ny = (unsigned)std::min<int64_t>(65535, nfolds - f0);
     MomentParams<T> q = mp;
-    if (mp.offsets) {
+    if (mp.ranges) q.ranges = mp.ranges + 2 * f0;
+    if (mp.offsets || mp.ranges) {
       q.fold0 = mp.fold0 + f0;
-      q.fs = mp.fs + f0;
+      q.fs = mp.fs ? mp.fs + f0 : nullptr;
       q.pw_cols = mp.pw_cols ? mp.pw_cols + f0 * 4 : nullptr;
-      q.stats = mp.stats + (size_t)f0 * 2 * mp.ld;
+      q.stats = mp.stats ? mp.stats + (size_t)f0 * 2 * mp.ld : nullptr;
       q.raw = mp.raw ? mp.raw + (size_t)f0 * 2 * mp.ld : nullptr;
     }
     q.grp0 = col_shard; q.grp_stride = n_col_shards;
@@ -386,7 +387,7 @@ int32_t join_stats(cvmx_t* h, cudaStream_t saved) {
 // concurrently - the chains store raw sums - and k_finalize_stats turns them into means / stds once both are done.
 template <typename T>
 int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, int64_t max_rows,
-                          int col_shard, int n_col_shards, double overlap_ns) {
+                          int col_shard, int n_col_shards, double overlap_ns, const T* have_raw = nullptr) {
   const size_t sz = sizeof(T);
   const int64_t ld = h->ld;
   CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
@@ -420,9 +421,11 @@ int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx,
   mp.flags = h->flags; mp.resolution = (T)h->resolution;
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = h->fscal.as<FoldScalars>(); mp.pw_cols = h->pwcols.as<T>(); mp.stats = h->stats.as<T>();
-  mp.raw = h->rawsums.as<T>();
-  int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards, overlap_ns);
-  if (rc) return rc;
+  mp.raw = have_raw ? const_cast<T*>(have_raw) : h->rawsums.as<T>();
+  if (!have_raw) {   // (have_raw: the fold sums were accumulated chunk by chunk during cvmx_fit_folds)
+    int32_t rc = launch_moments<T>(h, mp, Pn, max_rows, col_shard, n_col_shards, overlap_ns);
+    if (rc) return rc;
+  }
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0));
   mp.grp0 = 0; mp.grp_stride = 1;
   if (n_col_shards > 1) {
@@ -553,6 +556,8 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
     // device CSR); partial slots are numbered fold-major so that one pass sums them per fold
     bool fused = ff != nullptr && g0 == 0 && g1 == N && ff->P > 0;
     std::vector<int64_t> fold_base, fold_n;
+    std::vector<int64_t> h_ranges;      // [chunk][fold][2]: CSR positions of the fold's rows inside the chunk
+    std::vector<int64_t> chunk_fold_rows;   // [chunk]: longest fold slice
     if (fused) {
       const int64_t P = ff->P;
       struct Piece { int64_t lo, hi; int32_t fold; };
@@ -566,6 +571,9 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
           const int64_t* e = ff->idx + ff->off[f + 1];
           const int64_t lo = std::lower_bound(b, e, r0) - ff->idx, hi = std::lower_bound(b, e, r1) - ff->idx;
           const int64_t n = hi - lo;
+          h_ranges.push_back(lo); h_ranges.push_back(hi);
+          if (f == 0) chunk_fold_rows.push_back(0);
+          chunk_fold_rows.back() = std::max(chunk_fold_rows.back(), n);
           if (n <= 0) continue;
           const int64_t ns = (n + unit_rows - 1) / unit_rows, per = round_up((n + ns - 1) / ns, GBK);
           for (int64_t s2 = 0; s2 < ns; ++s2) {
@@ -627,6 +635,11 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
         pl.units.push_back(v);
       }
       CU(h, h->fold_gram.reserve((size_t)P * ntiles * GACC * GTHREADS * sizeof(double)));
+      // the folds' own column sums (numpy order = CSR order inside a fold) are continued chunk by chunk as well
+      CU(h, h->fold_raw.reserve((size_t)P * 2 * ld * sz));
+      CU(h, h->chunk_ranges.reserve(h_ranges.size() * sizeof(int64_t)));
+      CU(h, cudaMemsetAsync(h->fold_raw.p, 0, (size_t)P * 2 * ld * sz, h->stream));
+      CU(h, cudaMemcpyAsync(h->chunk_ranges.p, h_ranges.data(), h_ranges.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     }
     GramParams<T> gp;
     gp.Z = Z; gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = fused ? h->d_idx.as<int64_t>() : nullptr;
@@ -671,6 +684,14 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       mc.row0 = r0; mc.N = nr; mc.accumulate = c > 0;
       h->stream = stats_stream;
       rc = launch_moments<T>(h, mc, 1, nr);
+      if (!rc && fused && h->flags != 0) {
+        MomentParams<T> fc = mp;
+        fc.ranges = h->chunk_ranges.as<int64_t>() + (size_t)c * ff->P * 2;
+        fc.indices = h->d_idx.as<int64_t>();
+        fc.raw = h->fold_raw.as<T>(); fc.accumulate = 1;
+        fc.pw_cols = nullptr;
+        rc = launch_moments<T>(h, fc, ff->P, chunk_fold_rows[c]);
+      }
       h->stream = main_stream;
       if (rc) return rc;
       // the chunk's Gram partials
@@ -917,7 +938,8 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     // cvmx_fit_folds kept the raw Gram of every fold: only the statistics and the epilogue are left
     int64_t max_rows = 0;
     for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, off[f + 1] - off[f]);
-    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, max_rows, 0, 1, 0.0);
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, max_rows, 0, 1, 0.0,
+                                      h->flags ? h->fold_raw.as<T>() + (size_t)f0 * 2 * ld : nullptr);
     if (rc) return rc;
     std::vector<int2> tiles;
     plan_tiles(h, want, tiles);
@@ -1246,7 +1268,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
-                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram})
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }

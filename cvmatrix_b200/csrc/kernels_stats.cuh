@@ -226,6 +226,8 @@ struct MomentParams {
   int stages = 4;               // ring depth of k_moments_pipe (runtime: few long chains want more bytes in flight)
   int64_t row0 = 0;             // fit mode: rows [row0, row0 + N) ...
   int accumulate = 0;           // ... continuing the chains stored in sum_z / sumsq_z (chunk-pipelined fit)
+  const int64_t* ranges = nullptr;   // fold mode, optional: [fold][2] = begin, end positions in `indices` (a slice of the
+                                     // fold's rows: chunk-pipelined fit + folds), instead of offsets[fold0 + fold]
   const int* scan_ok = nullptr; // [folds][scan_groups]: groups already finished by the binade scan (kernels_scan.cuh);
   int scan_groups = 0;          // k_moments_pipe skips them
 };
@@ -235,7 +237,7 @@ __device__ __forceinline__ void finalize_column(const MomentParams<T>& p, int64_
   const int64_t C = p.K + p.M;
   if (c >= C) return;
   const bool isX = c < p.K;
-  if (p.offsets && p.raw) {  // deferred: k_finalize_stats turns the sums into mean / std once the fold scalars exist
+  if ((p.offsets || p.ranges) && p.raw) {  // deferred: k_finalize_stats turns the sums into mean / std once the fold scalars exist
     T* o = p.raw + (size_t)f * 2 * p.ld;
     o[c] = s;
     o[p.ld + c] = q;
@@ -245,7 +247,7 @@ __device__ __forceinline__ void finalize_column(const MomentParams<T>& p, int64_
     if (isX && p.K == 1) { s = p.pw_cols[f * 4 + 0]; q = p.pw_cols[f * 4 + 1]; }
     if (!isX && p.M == 1) { s = p.pw_cols[f * 4 + 2]; q = p.pw_cols[f * 4 + 3]; }
   }
-  if (!p.offsets) {  // fit mode
+  if (!p.offsets && !p.ranges) {  // fit mode
     p.sum_z[c] = s;
     p.sumsq_z[c] = q;
     return;
@@ -280,11 +282,14 @@ __global__ void __launch_bounds__(128) k_moments_direct(MomentParams<T> p) {
   const int64_t f = blockIdx.y;
   const int64_t c = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * 128 + threadIdx.x;
   if (c >= p.ld) return;
-  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
-  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
-  const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
+  const int64_t beg = p.ranges ? p.ranges[2 * f] : (p.offsets ? p.offsets[p.fold0 + f] : 0);
+  const int64_t n = p.ranges ? p.ranges[2 * f + 1] - beg : (p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N);
+  const int64_t* idx = (p.offsets || p.ranges) ? p.indices + beg : nullptr;
   T s = T(0), q = T(0);
-  if (p.accumulate) { s = p.sum_z[c]; q = p.sumsq_z[c]; }
+  if (p.accumulate) {
+    if (p.ranges) { s = p.raw[(size_t)f * 2 * p.ld + c]; q = p.raw[(size_t)f * 2 * p.ld + p.ld + c]; }
+    else { s = p.sum_z[c]; q = p.sumsq_z[c]; }
+  }
   int64_t i = 0;
   for (; i + 4 <= n; i += 4) {
     int64_t r[4]; T z[4], wv[4];
@@ -341,9 +346,9 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   const int64_t f = blockIdx.y;
   if (p.scan_ok && p.scan_ok[f * p.scan_groups + (p.grp0 + blockIdx.x * p.grp_stride)]) return;   // whole CTA
   const int64_t c0 = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * MOM_COLS;
-  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
-  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
-  const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
+  const int64_t beg = p.ranges ? p.ranges[2 * f] : (p.offsets ? p.offsets[p.fold0 + f] : 0);
+  const int64_t n = p.ranges ? p.ranges[2 * f + 1] - beg : (p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N);
+  const int64_t* idx = (p.offsets || p.ranges) ? p.indices + beg : nullptr;
   const int64_t nst = (n + MOM_ROWS - 1) / MOM_ROWS;
 
   if (tid == 0) {
@@ -353,7 +358,10 @@ __global__ void __launch_bounds__(MOM_THREADS) k_moments_pipe(MomentParams<T> p)
   __syncthreads();
 
   T acc = T(0);
-  if (p.accumulate && warp < 2) acc = warp == 0 ? p.sum_z[c0 + lane] : p.sumsq_z[c0 + lane];
+  if (p.accumulate && warp < 2) {
+    if (p.ranges) acc = p.raw[(size_t)f * 2 * p.ld + (warp == 0 ? 0 : p.ld) + c0 + lane];   // fold slices continue the fold's raw sums
+    else acc = warp == 0 ? p.sum_z[c0 + lane] : p.sumsq_z[c0 + lane];
+  }
   if (warp >= 2) {
     // ---------------- producers: warp 2 + pw owns rows [PROWS pw, PROWS (pw + 1)) of every stage ----------------
     // A warp-wide cp.async covers RPI whole row segments (coalesced 16-byte chunks); the byte offset of each row is
