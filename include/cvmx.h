@@ -175,8 +175,8 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val_idx, int64_t n_val, 
 /*
  * Sharded evaluation of a fold batch across several handles (one per GPU / rank).  The path shards two ways
  * (SURVEY.md 8e): many folds -> give each rank its own fold range with cvmx_training_batch (no collective);
- * few large folds -> split every fold's ROWS across ranks with the three phases below, the caller doing the two
- * all-reduces (NCCL) in between.  All pointers are DEVICE pointers; every rank holds the full data and the CSR.
+ * few large folds -> split every fold's ROWS across ranks with the three phases below, the caller all-reducing
+ * (NCCL) the two buffers in between - one fused all-reduce in cvmatrix_b200/distributed.py.  All pointers are DEVICE pointers; every rank holds the full data and the CSR.
  *   1. cvmx_sharded_stats : statistics of folds [f0, f1) for column groups col_shard, col_shard + n_col_shards, ...
  *        (the sequential per-column chains cannot be split by rows, so they are split by columns).  Returns the
  *        device address / element count (handle dtype) of the [P'][2][ld] buffer: entries of other shards are zero,

@@ -89,3 +89,36 @@ def test_fused_falls_back_quietly():
     p = lambda a: a.ctypes.data  # noqa: E731
     rc = m2._lib.cvmx_fit_folds(m2._h, p(X2), N, K, K, None, 0, 0, None, _lib.HOST, p(off), p(idx), 2, 0)
     assert rc == 0 and m2._lib.cvmx_folds_are_cached(m2._h) == 0
+
+
+@pytest.mark.parametrize("dtype,weighted,has_Y", [(np.float32, True, True), (np.float64, False, False), (np.float64, True, False)])
+def test_fused_variants(dtype, weighted, has_Y):
+    """float32, unweighted and X-only fits take the fused path too and agree with the two-pass path."""
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    N, K, M, P = 300_000, 64, 2, 4
+    rng = np.random.default_rng(41)
+    X = rng.random((N, K)).astype(dtype)
+    Y = rng.random((N, M)).astype(dtype) if has_Y else None
+    w = rng.random(N).astype(dtype) if weighted else None
+    part = Partitioner(np.arange(N) % P)
+    flags = dict(center_X=False, center_Y=False) if dtype == np.float32 else {}   # float32: un-centred (SURVEY.md Appendix B)
+    a = CVMatrix(dtype=dtype, copy=False, **flags)
+    a.fit(X, Y, w, folds=part)
+    assert a.folds_cached
+    b = CVMatrix(dtype=dtype, copy=False, **flags)
+    b.fit(X, Y, w)
+    b.set_folds(part)
+    kw = dict(return_XTY=has_Y, out="numpy")
+    ra, rb = a.training_batch(**kw), b.training_batch(**kw)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    assert rel_fro(a.XTX, b.XTX) <= tol
+    for f in range(P):
+        assert rel_fro(ra["XTX"][f], rb["XTX"][f]) <= tol
+        if has_Y:
+            assert rel_fro(ra["XTY"][f], rb["XTY"][f]) <= tol
+        for s in STATS:
+            assert (ra[s] is None) == (rb[s] is None)
+            if ra[s] is not None:
+                assert np.array_equal(ra[s][f], rb[s][f])
+    assert np.array_equal(ra["sum_w_train"], rb["sum_w_train"]) and np.array_equal(ra["status"], rb["status"])
