@@ -226,6 +226,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION / INFO print to stdout; the contract is ONE JSON line there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -446,7 +449,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": (f"rows of each fold sharded x{world} + 1 NCCL all-reduce" if row_sharded else f"fold-sharded x{world}"),
+            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": ((f"rows of each fold sharded x{world} + " + ("peer-memory reduction over NVLink (symmetric memory, no all-reduce)" if (sf is not None and sf._symm is not None) else "1 NCCL all-reduce")) if row_sharded else f"fold-sharded x{world}"),
                        "l2_policy": "inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8 else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2",
                        "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

@@ -76,6 +76,7 @@ struct cvmx_handle {
   int scan_mode = 1;
   // fused fit + folds (cvmx_fit_folds): raw float64 Gram of every fold of a true partition, [P][ntiles][GACC][GTHREADS],
   // valid while csr_version == fold_gram_version; cvmx_training_batch then only runs statistics + epilogue
+  DevBuf peer_ptrs;
   DevBuf fold_gram, fold_raw, chunk_ranges;   // fold_raw: [P][2][ld] raw column sums of every fold, same validity
   int64_t fold_gram_version = -1;
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
@@ -923,7 +924,8 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
 }
 
 template <typename T>
-int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy);
+int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy,
+                       const double* const* peers = nullptr, int npeers = 0);
 
 // ---- folds -----------------------------------------------------------------------------------------
 // Runs folds [f0, f1) of the CSR (d_off/d_idx on device, off on host) and leaves results in device
@@ -1085,7 +1087,8 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
 // phase 3: epilogue of folds [f0, f1) from (all-reduced) raw Grams in the fragment layout of phase 2; `first` is
 // the fold of the batch that gram[0] belongs to (a rank may finish only the folds it owns)
 template <typename T>
-int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy) {
+int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy,
+                       const double* const* peers, int npeers) {
   const int64_t Pn = f1 - f0;
   if (Pn <= 0) return CVMX_OK;
   Plan pl;
@@ -1119,6 +1122,8 @@ int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint
   gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = const_cast<double*>(gram); gp.raw_out = nullptr; gp.force_partials = 0;
   gp.epi = epi;
+  for (int q = 0; q < npeers && q < 8; ++q) gp.peers[q] = peers[q];
+  gp.npeers = std::min(npeers, 8);
   const size_t smem = gram_smem_bytes<T>();
   const int ev0 = prof_mark(h);
   k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
@@ -1268,7 +1273,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
-                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
+                    &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges, &h->peer_ptrs})
     b->release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
@@ -1524,6 +1529,39 @@ int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1,
       k_pack_scalars<double><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>() + d, Pn, (double*)oscal, ostatus);
     else
       k_pack_scalars<float><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>() + d, Pn, (float*)oscal, ostatus);
+    h->launches++;
+    CU(h, cudaGetLastError());
+  }
+  return CVMX_OK;
+}
+
+
+int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1, int64_t f0, int64_t f1, uint32_t want,
+                                  const void* const* peer_bufs, int32_t n_peers, int64_t gram_count, void* oxx, void* oxy, void* ostats,
+                                  void* oscal, int32_t* ostatus) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: fit first");
+  if (batch_f0 < 0 || f0 < batch_f0 || f1 > batch_f1 || batch_f1 > h->P || f0 > f1 || !peer_bufs || n_peers < 1 || n_peers > 8)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: bad fold range or peer list (at most 8 peers)");
+  if (h->dtype != CVMX_F64) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: float64 handles only");
+  CU(h, cudaSetDevice(h->device));
+  // statistics rows of the whole batch: sum of the peers' column shards, straight into the statistics buffer
+  const int64_t nst = (batch_f1 - batch_f0) * 2 * h->ld;
+  CU(h, h->peer_ptrs.reserve(8 * sizeof(void*)));
+  CU(h, cudaMemcpyAsync(h->peer_ptrs.p, peer_bufs, n_peers * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
+  k_peer_sum_rows<double><<<(unsigned)((nst + 255) / 256), 256, 0, h->stream>>>(h->peer_ptrs.as<const double*>(), n_peers, gram_count, nst,
+                                                                              h->stats.as<double>());
+  h->launches++;
+  CU(h, cudaGetLastError());
+  int32_t rc = sharded_finish<double>(h, batch_f0, f0, f1, want, (const double*)peer_bufs[0], (double*)oxx, (double*)oxy,
+                                      (const double* const*)peer_bufs, n_peers);
+  if (rc || f1 == f0) return rc;
+  const size_t sz = 8;
+  const int64_t C = h->K + h->M, d = f0 - batch_f0, Pn = f1 - f0;
+  if (ostats)
+    CU(h, cudaMemcpy2DAsync(ostats, C * sz, h->stats.as<char>() + (size_t)d * 2 * h->ld * sz, h->ld * sz, C * sz, Pn * 2,
+                            cudaMemcpyDeviceToDevice, h->stream));
+  if (oscal || ostatus) {
+    k_pack_scalars<double><<<(unsigned)((Pn + 255) / 256), 256, 0, h->stream>>>(h->fscal.as<FoldScalars>() + d, Pn, (double*)oscal, ostatus);
     h->launches++;
     CU(h, cudaGetLastError());
   }

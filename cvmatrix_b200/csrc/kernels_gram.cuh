@@ -73,6 +73,10 @@ struct GramParams {
                            // instead of running the epilogue (multi-GPU: all-reduced across ranks, then finished)
   int force_partials;      // k_gram: write partials even for single-unit folds
   EpiParams<T> epi;
+  // k_gram_reduce, multi-GPU: the fold's raw Gram lives in npeers buffers of the same layout - this GPU's and its
+  // peers', mapped over NVLink (symmetric memory) - and the owner sums them on the fly instead of an all-reduce
+  const double* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int npeers = 0;
 };
 
 template <typename T>
@@ -432,7 +436,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
   const GramUnit unit = p.units[fold_units[fold]];
   const int2 tl = p.tiles[tile];
   double acc[8][4][2];
-  const double* src = p.partials + ((size_t)unit.part_base * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
+  const size_t tile_off = ((size_t)unit.part_base * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
+  const double* src = (p.npeers > 0 ? p.peers[0] : p.partials) + tile_off;
   const size_t split_stride = (size_t)p.ntiles * GACC * GTHREADS;
 #pragma unroll
   for (int t = 0; t < 8; ++t)
@@ -441,15 +446,28 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
       acc[t][u][0] = src[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
       acc[t][u][1] = src[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
     }
-  for (int s = 1; s < unit.nsplit; ++s) {
-    const double* ps = src + s * split_stride;
+  if (p.npeers > 0) {
+    for (int q = 1; q < p.npeers; ++q) {   // peer order: deterministic
+      const double* ps = p.peers[q] + tile_off;
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
+      for (int t = 0; t < 8; ++t)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
-        acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
-      }
+        for (int u = 0; u < 4; ++u) {
+          acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
+          acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
+        }
+    }
+  } else {
+    for (int s = 1; s < unit.nsplit; ++s) {
+      const double* ps = src + s * split_stride;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
+          acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
+        }
+    }
   }
   if (p.raw_out) {
     double* dst = p.raw_out + ((size_t)unit.fold * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
@@ -489,6 +507,17 @@ __global__ void __launch_bounds__(256) k_partial_sum(const double* __restrict__ 
     acc.x += v.x; acc.y += v.y;
   }
   *reinterpret_cast<double2*>(out + ((size_t)unit.fold * ntiles + tile) * tile_elems + e) = acc;
+}
+
+// Statistics rows of a column-sharded evaluation: every rank holds its own column groups (zeros elsewhere) behind its
+// raw Grams in the symmetric buffer; out[i] = sum over peers, read over NVLink (replaces the second all-reduce).
+template <typename T>
+__global__ void k_peer_sum_rows(const double* const* __restrict__ peers, int npeers, int64_t offset, int64_t n, T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0.0;
+  for (int q = 0; q < npeers; ++q) v += peers[q][offset + i];
+  out[i] = (T)v;
 }
 
 // CSR index normalisation: numpy wrap-around for negative indices, error flag for out-of-range ones.

@@ -44,6 +44,14 @@ class ShardedFolds:
         self.dev = torch.device("cuda", cvm.device)
         self.tdt = torch.float64 if np.dtype(cvm.dtype) == np.float64 else torch.float32
         self._gram: Optional["torch.Tensor"] = None
+        # peer-memory reduction (float64, <= 8 ranks): the raw Grams live in symmetric memory mapped over NVLink and the
+        # fold owner sums its peers' fragments inside the epilogue kernel - no all-reduce.  CVMX_PEER_REDUCE=0 disables.
+        import os
+
+        self.use_peers = (os.environ.get("CVMX_PEER_REDUCE", "1") != "0" and self.world > 1 and self.world <= 8
+                          and self.tdt == torch.float64)
+        self._symm = None        # (buffer, handle, elements per half, peer pointer arrays per half)
+        self._step = 0
 
     def alloc_outputs(self, n_folds: int):
         t, K, M = self.torch, self.cvm.K, self.cvm.M or 0
@@ -76,6 +84,22 @@ class ShardedFolds:
         shards = self.emulate_shards or self.world
         _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, shards, C.byref(sp), C.byref(sc)), h)
         n = lib.cvmx_sharded_gram_count(h, f0, f1, 3)
+        half_elems = n + sc.value
+        if self.use_peers and self.world > 1 and (self._symm is None or self._symm[2] < half_elems):
+            self._symm = self._setup_symm(half_elems)
+        if self._symm is not None and self.world > 1:
+            buf, hdl, cap, ptrs = self._symm
+            half = self._step & 1            # two halves alternate: a peer may still read step i while step i + 1 is written
+            self._step += 1
+            gram = buf[half * cap: half * cap + n]
+            _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, shards, vp(gram)), h)
+            _lib.check(lib.cvmx_sharded_stats_wait(h), h)
+            stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8"), device=self.dev)
+            buf[half * cap + n: half * cap + n + sc.value].copy_(stats)
+            hdl.barrier(channel=0)           # every rank's Grams and statistics rows are complete and visible
+            _lib.check(lib.cvmx_sharded_finish_peers(h, f0, f1, o0, o1, 3, ptrs[half], self.world, n, vp(out["XTX"]), vp(out["XTY"]),
+                                                     vp(out["stats"]), vp(out["scal"]), vp(out["status"])), h)
+            return dict(out, fold_begin=o0, fold_end=o1)
         # one buffer for both reductions: [raw Grams | statistics rows widened to float64] -> ONE all-reduce
         if self._gram is None or self._gram.numel() < n + sc.value:
             self._gram = t.empty((n + sc.value,), dtype=t.float64, device=self.dev)
@@ -91,6 +115,35 @@ class ShardedFolds:
         _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
                                            vp(out["scal"]), vp(out["status"])), h)
         return dict(out, fold_begin=o0, fold_end=o1)
+
+
+def _symm_setup(self, half_elems: int):
+    """Symmetric-memory buffer of 2 x half_elems float64 shared by all ranks of the group; returns None (on every rank)
+    unless every rank succeeded, so that all ranks take the same path."""
+    t, dist = self.torch, self.dist
+    ok, res = 1, None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        buf = symm_mem.empty(2 * half_elems, dtype=t.float64, device=self.dev)
+        hdl = symm_mem.rendezvous(buf, grp)
+        ptrs = []
+        for half in range(2):
+            arr = (C.c_void_p * self.world)(*[int(p) + half * half_elems * 8 for p in hdl.buffer_ptrs])
+            ptrs.append(arr)
+        res = (buf, hdl, half_elems, ptrs)
+    except Exception:   # pragma: no cover - depends on the box (driver support for shareable allocations)
+        ok = 0
+    flag = t.tensor([ok], dtype=t.int32, device=self.dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+    if int(flag.item()) == 0:
+        self.use_peers = False
+        return None
+    return res
+
+
+ShardedFolds._setup_symm = _symm_setup
 
 
 def fit_row_sharded(cvm: CVMatrix, X, Y=None, weights=None, group=None) -> None:

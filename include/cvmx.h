@@ -197,6 +197,16 @@ int32_t cvmx_sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int3
 int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram_dev,
                             void* out_XTX, void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status);
 
+/* Phase 3 without the all-reduce: the raw Grams (and, behind them at element gram_count, the statistics rows widened to
+ * float64) of ALL ranks live in buffers of the same layout that are mapped into this process over NVLink (symmetric
+ * memory; peer_bufs[q] = rank q's buffer, this rank's own included, at most 8).  The owner of folds [f0, f1) sums the
+ * peers' fragments on the fly inside the epilogue kernel (P2P loads) and the peers' statistics rows for the batch
+ * [batch_f0, batch_f1) with a small kernel.  The caller provides the cross-GPU barrier between phase 2 and this call
+ * (cvmatrix_b200/distributed.py: symmetric-memory barrier).  float64 handles. */
+int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1, int64_t f0, int64_t f1, uint32_t want,
+                                  const void* const* peer_bufs, int32_t n_peers, int64_t gram_count, void* out_XTX,
+                                  void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, CUDA events are recorded on the
  * handle's stream around the statistics kernels (ms[0]), the Gram kernel (ms[1]) and the split-reduce
  * kernel (ms[2]); cvmx_profile_read synchronises, returns the accumulated milliseconds and span counts

@@ -30,17 +30,24 @@ m.set_folds(part)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 _lib.check(m._lib.cvmx_set_stream(m._h, C.c_void_p(stream.cuda_stream)), m._h)
-sf = ShardedFolds(m)
-for row_sharded in (True, False):
-    out = sf.training_batch(0, 3, row_sharded=row_sharded)
-    torch.cuda.synchronize()
-    for pos, f in enumerate(range(out["fold_begin"], out["fold_end"])):
-        r = orc.fold(part.get_validation_indices(f))
-        K = 200
-        assert rel_fro(out["XTX"][pos].cpu().numpy(), r.XTX) <= 1e-12, (row_sharded, f)
-        assert rel_fro(out["XTY"][pos].cpu().numpy(), r.XTY) <= 1e-12, (row_sharded, f)
-        assert np.array_equal(out["stats"][pos, 0, :K].cpu().numpy(), r.X_mean[0]), (row_sharded, f)
-        assert np.array_equal(out["stats"][pos, 1, K:].cpu().numpy(), r.Y_std[0]), (row_sharded, f)
+modes = []
+for use_peers in (True, False):       # peer-memory reduction over NVLink (symmetric memory) and the NCCL all-reduce path
+    sf = ShardedFolds(m)
+    sf.use_peers = sf.use_peers and use_peers
+    for row_sharded in (True, False):
+        for rep in range(3):          # several steps: the symmetric buffer alternates between its two halves
+            out = sf.training_batch(0, 3, row_sharded=row_sharded)
+        torch.cuda.synchronize()
+        for pos, f in enumerate(range(out["fold_begin"], out["fold_end"])):
+            r = orc.fold(part.get_validation_indices(f))
+            K = 200
+            assert rel_fro(out["XTX"][pos].cpu().numpy(), r.XTX) <= 1e-12, (use_peers, row_sharded, f)
+            assert rel_fro(out["XTY"][pos].cpu().numpy(), r.XTY) <= 1e-12, (use_peers, row_sharded, f)
+            assert np.array_equal(out["stats"][pos, 0, :K].cpu().numpy(), r.X_mean[0]), (use_peers, row_sharded, f)
+            assert np.array_equal(out["stats"][pos, 1, K:].cpu().numpy(), r.Y_std[0]), (use_peers, row_sharded, f)
+    modes.append(sf._symm is not None)
+if rank == 0:
+    print("PEER_REDUCE_USED", modes)
 owned = torch.zeros(3, device="cuda")
 owned[out["fold_begin"]:out["fold_end"]] += 1
 dist.all_reduce(owned)
