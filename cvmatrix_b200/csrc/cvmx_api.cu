@@ -44,6 +44,16 @@ struct Plan {                 // launch plan of one fold range (cached)
   int64_t max_rows = 0;
 };
 
+// Device copies of a launch plan that repeats from step to step (sharded phases): re-uploading four small tables
+// costs four DMA operations on the critical path of every step.
+struct TableCache {
+  std::vector<int64_t> key;
+  DevBuf units, tiles, fold_units, split_folds;
+  int64_t n_units = 0, n_partial_units = 0;
+  int ntiles = 0;
+  void release() { units.release(); tiles.release(); fold_units.release(); split_folds.release(); key.clear(); }
+};
+
 }  // namespace
 
 struct cvmx_handle {
@@ -77,6 +87,7 @@ struct cvmx_handle {
   // fused fit + folds (cvmx_fit_folds): raw float64 Gram of every fold of a true partition, [P][ntiles][GACC][GTHREADS],
   // valid while csr_version == fold_gram_version; cvmx_training_batch then only runs statistics + epilogue
   DevBuf peer_ptrs;
+  TableCache tc_gram, tc_finish;
   DevBuf fold_gram, fold_raw, chunk_ranges;   // fold_raw: [P][2][ld] raw column sums of every fold, same validity
   int64_t fold_gram_version = -1;
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
@@ -989,6 +1000,20 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   return CVMX_OK;
 }
 
+int32_t upload_tables(cvmx_t* h, TableCache& tc, const std::vector<int64_t>& key, const Plan& pl) {
+  CU(h, tc.units.reserve(std::max<size_t>(1, pl.units.size()) * sizeof(GramUnit)));
+  CU(h, tc.tiles.reserve(std::max<size_t>(1, pl.tiles.size()) * sizeof(int2)));
+  CU(h, tc.fold_units.reserve(std::max<size_t>(1, pl.fold_units.size()) * sizeof(int32_t)));
+  CU(h, tc.split_folds.reserve(std::max<size_t>(1, pl.split_folds.size()) * sizeof(int32_t)));
+  CU(h, cudaMemcpyAsync(tc.units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(tc.tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(tc.fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(tc.split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  tc.key = key;
+  tc.n_units = (int64_t)pl.units.size(); tc.n_partial_units = pl.n_partial_units; tc.ntiles = (int)pl.tiles.size();
+  return CVMX_OK;
+}
+
 // ---- sharded evaluation (multi-GPU: one handle per rank, collectives done by the caller) -------------------------
 // phase 1: statistics of folds [f0, f1) restricted to column groups col_shard, col_shard + n, ... ; the other
 //          entries of the stats buffer stay zero, so an all-reduce(sum) across ranks assembles the full rows.
@@ -1012,57 +1037,53 @@ int32_t sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int col_shard, int n_co
 template <typename T>
 int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard, int nshards, double* out) {
   const int64_t Pn = f1 - f0;
-  Plan pl;
-  plan_tiles(h, want, pl.tiles);
-  const int ntiles = (int)pl.tiles.size();
-  // shard boundaries inside each fold's index range, aligned to the stage size
-  std::vector<int64_t> off2(2 * Pn);
-  int64_t total = 0;
-  for (int64_t f = 0; f < Pn; ++f) {
-    const int64_t beg = h->h_off[f0 + f], n = h->h_off[f0 + f + 1] - beg;
-    const int64_t per = round_up((n + nshards - 1) / nshards, GBK);
-    off2[2 * f] = beg + std::min(n, shard * per);
-    off2[2 * f + 1] = beg + std::min(n, (shard + 1) * per);
-    total += off2[2 * f + 1] - off2[2 * f];
-  }
-  // units: split each fold's shard so the grid fills the SMs in whole waves
-  const int64_t sms = h->sm_count;
-  int64_t best_R = 4096; double best = -1;
-  for (int64_t R = 1024; R <= 4096; R += GBK) {
-    int64_t items = 0;
-    for (int64_t f = 0; f < Pn; ++f) items += std::max<int64_t>(1, (off2[2 * f + 1] - off2[2 * f] + R - 1) / R);
-    items *= ntiles;
-    const double eff = (double)items / (double)(sms * ((items + sms - 1) / sms));
-    if (eff > best + 1e-9) { best = eff; best_R = R; }
-  }
-  pl.fold_units.assign(Pn, 0);
-  for (int64_t f = 0; f < Pn; ++f) {
-    const int64_t beg = off2[2 * f], n = off2[2 * f + 1] - beg;
-    const int64_t ns = std::max<int64_t>(1, (n + best_R - 1) / best_R);
-    const int64_t per = round_up((n + ns - 1) / ns, GBK);
-    pl.fold_units[f] = (int32_t)pl.units.size();
-    pl.split_folds.push_back((int32_t)f);
-    for (int64_t s2 = 0; s2 < ns; ++s2) {
-      GramUnit u;
-      u.row_begin = beg + std::min(n, s2 * per); u.row_end = beg + std::min(n, (s2 + 1) * per);
-      u.fold = (int32_t)f; u.split = (int32_t)s2; u.nsplit = (int32_t)ns; u.part_base = (int32_t)pl.n_partial_units;
-      pl.units.push_back(u);
+  TableCache& tc = h->tc_gram;
+  const std::vector<int64_t> key = {f0, f1, (int64_t)want, shard, nshards, h->csr_version};
+  if (tc.key != key) {
+    Plan pl;
+    plan_tiles(h, want, pl.tiles);
+    const int nt = (int)pl.tiles.size();
+    // shard boundaries inside each fold's index range, aligned to the stage size
+    std::vector<int64_t> off2(2 * Pn);
+    for (int64_t f = 0; f < Pn; ++f) {
+      const int64_t beg = h->h_off[f0 + f], n = h->h_off[f0 + f + 1] - beg;
+      const int64_t per = round_up((n + nshards - 1) / nshards, GBK);
+      off2[2 * f] = beg + std::min(n, shard * per);
+      off2[2 * f + 1] = beg + std::min(n, (shard + 1) * per);
     }
-    pl.n_partial_units += ns;
+    // units: split each fold's shard so the grid fills the SMs in whole waves
+    const int64_t sms = h->sm_count;
+    int64_t best_R = 4096; double best = -1;
+    for (int64_t R = 1024; R <= 4096; R += GBK) {
+      int64_t items = 0;
+      for (int64_t f = 0; f < Pn; ++f) items += std::max<int64_t>(1, (off2[2 * f + 1] - off2[2 * f] + R - 1) / R);
+      items *= nt;
+      const double eff = (double)items / (double)(sms * ((items + sms - 1) / sms));
+      if (eff > best + 1e-9) { best = eff; best_R = R; }
+    }
+    pl.fold_units.assign(Pn, 0);
+    for (int64_t f = 0; f < Pn; ++f) {
+      const int64_t beg = off2[2 * f], n = off2[2 * f + 1] - beg;
+      const int64_t ns = std::max<int64_t>(1, (n + best_R - 1) / best_R);
+      const int64_t per = round_up((n + ns - 1) / ns, GBK);
+      pl.fold_units[f] = (int32_t)pl.units.size();
+      pl.split_folds.push_back((int32_t)f);
+      for (int64_t s2 = 0; s2 < ns; ++s2) {
+        GramUnit u;
+        u.row_begin = beg + std::min(n, s2 * per); u.row_end = beg + std::min(n, (s2 + 1) * per);
+        u.fold = (int32_t)f; u.split = (int32_t)s2; u.nsplit = (int32_t)ns; u.part_base = (int32_t)pl.n_partial_units;
+        pl.units.push_back(u);
+      }
+      pl.n_partial_units += ns;
+    }
+    int32_t rcu = upload_tables(h, tc, key, pl);   // the plan repeats from step to step: uploaded once
+    if (rcu) return rcu;
   }
-  (void)total;
-  CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
-  CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
-  CU(h, h->fold_units.reserve(pl.fold_units.size() * sizeof(int32_t)));
-  CU(h, h->split_folds.reserve(pl.split_folds.size() * sizeof(int32_t)));
-  CU(h, h->partials.reserve((size_t)pl.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
-  CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  const int ntiles = tc.ntiles;
+  CU(h, h->partials.reserve((size_t)tc.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
   GramParams<T> gp;
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = h->d_idx.as<int64_t>();
-  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.units = tc.units.as<GramUnit>(); gp.tiles = tc.tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = h->partials.as<double>(); gp.raw_out = out; gp.force_partials = 1;
   gp.epi = EpiParams<T>();
   const size_t smem = gram_smem_bytes<T>();
@@ -1072,12 +1093,12 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
     h->attr_gram = true;
   }
   const int ev0 = prof_mark(h);
-  k_gram<T><<<(unsigned)(pl.units.size() * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+  k_gram<T><<<(unsigned)(tc.n_units * ntiles), GLAUNCH, smem, h->stream>>>(gp);
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
   k_partial_sum<<<dim3((unsigned)(GACC * GTHREADS / 512), (unsigned)ntiles, (unsigned)Pn), 256, 0, h->stream>>>(
-      h->partials.as<double>(), h->units.as<GramUnit>(), h->fold_units.as<int32_t>(), ntiles, out);
+      h->partials.as<double>(), tc.units.as<GramUnit>(), tc.fold_units.as<int32_t>(), ntiles, out);
   h->launches++;
   prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
   CU(h, cudaGetLastError());
@@ -1091,25 +1112,23 @@ int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint
                        const double* const* peers, int npeers) {
   const int64_t Pn = f1 - f0;
   if (Pn <= 0) return CVMX_OK;
-  Plan pl;
-  plan_tiles(h, want, pl.tiles);
-  const int ntiles = (int)pl.tiles.size();
-  pl.fold_units.assign(f1 - batch_f0, 0);
-  for (int64_t f = batch_f0; f < f1; ++f) {
-    GramUnit u;
-    u.row_begin = u.row_end = 0; u.fold = (int32_t)(f - batch_f0); u.split = 0; u.nsplit = 1; u.part_base = (int32_t)(f - batch_f0);
-    pl.fold_units[f - batch_f0] = (int32_t)pl.units.size();
-    pl.units.push_back(u);
-    if (f >= f0) pl.split_folds.push_back((int32_t)(f - batch_f0));
+  TableCache& tc = h->tc_finish;
+  const std::vector<int64_t> key = {batch_f0, f0, f1, (int64_t)want, h->csr_version};
+  if (tc.key != key) {
+    Plan pl;
+    plan_tiles(h, want, pl.tiles);
+    pl.fold_units.assign(f1 - batch_f0, 0);
+    for (int64_t f = batch_f0; f < f1; ++f) {
+      GramUnit u;
+      u.row_begin = u.row_end = 0; u.fold = (int32_t)(f - batch_f0); u.split = 0; u.nsplit = 1; u.part_base = (int32_t)(f - batch_f0);
+      pl.fold_units[f - batch_f0] = (int32_t)pl.units.size();
+      pl.units.push_back(u);
+      if (f >= f0) pl.split_folds.push_back((int32_t)(f - batch_f0));
+    }
+    int32_t rcu = upload_tables(h, tc, key, pl);
+    if (rcu) return rcu;
   }
-  CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
-  CU(h, h->tiles.reserve(pl.tiles.size() * sizeof(int2)));
-  CU(h, h->fold_units.reserve(pl.fold_units.size() * sizeof(int32_t)));
-  CU(h, h->split_folds.reserve(pl.split_folds.size() * sizeof(int32_t)));
-  CU(h, cudaMemcpyAsync(h->units.p, pl.units.data(), pl.units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->tiles.p, pl.tiles.data(), pl.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->fold_units.p, pl.fold_units.data(), pl.fold_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  const int ntiles = tc.ntiles;
   EpiParams<T> epi;
   epi.mode = 1; epi.flags = h->flags; epi.want = want;
   epi.K = h->K; epi.M = h->M; epi.ld = h->ld;
@@ -1119,14 +1138,14 @@ int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint
   epi.out_xy = oxy ? oxy - (f0 - batch_f0) * h->K * h->M : nullptr; epi.xy_pitch = h->M; epi.xy_stride = h->K * h->M;
   GramParams<T> gp;
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = nullptr;
-  gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
+  gp.units = tc.units.as<GramUnit>(); gp.tiles = tc.tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = const_cast<double*>(gram); gp.raw_out = nullptr; gp.force_partials = 0;
   gp.epi = epi;
   for (int q = 0; q < npeers && q < 8; ++q) gp.peers[q] = peers[q];
   gp.npeers = std::min(npeers, 8);
   const size_t smem = gram_smem_bytes<T>();
   const int ev0 = prof_mark(h);
-  k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, h->fold_units.as<int32_t>(), h->split_folds.as<int32_t>());
+  k_gram_reduce<T><<<dim3(ntiles, (unsigned)Pn), GTHREADS, smem, h->stream>>>(gp, tc.fold_units.as<int32_t>(), tc.split_folds.as<int32_t>());
   h->launches++;
   prof_span(h, PROF_REDUCE, ev0, prof_mark(h));
   CU(h, cudaGetLastError());
@@ -1275,6 +1294,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges, &h->peer_ptrs})
     b->release();
+  h->tc_gram.release(); h->tc_finish.release();
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
   if (h->aux2_stream) { cudaStreamSynchronize(h->aux2_stream); cudaStreamDestroy(h->aux2_stream); }
@@ -1546,10 +1566,9 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
   CU(h, cudaSetDevice(h->device));
   // statistics rows of the whole batch: sum of the peers' column shards, straight into the statistics buffer
   const int64_t nst = (batch_f1 - batch_f0) * 2 * h->ld;
-  CU(h, h->peer_ptrs.reserve(8 * sizeof(void*)));
-  CU(h, cudaMemcpyAsync(h->peer_ptrs.p, peer_bufs, n_peers * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
-  k_peer_sum_rows<double><<<(unsigned)((nst + 255) / 256), 256, 0, h->stream>>>(h->peer_ptrs.as<const double*>(), n_peers, gram_count, nst,
-                                                                              h->stats.as<double>());
+  PeerList pl8;
+  for (int q = 0; q < 8; ++q) pl8.p[q] = q < n_peers ? (const double*)peer_bufs[q] : nullptr;
+  k_peer_sum_rows<double><<<(unsigned)((nst + 255) / 256), 256, 0, h->stream>>>(pl8, n_peers, gram_count, nst, h->stats.as<double>());
   h->launches++;
   CU(h, cudaGetLastError());
   int32_t rc = sharded_finish<double>(h, batch_f0, f0, f1, want, (const double*)peer_bufs[0], (double*)oxx, (double*)oxy,

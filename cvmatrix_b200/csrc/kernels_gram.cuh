@@ -447,16 +447,22 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
       acc[t][u][1] = src[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
     }
   if (p.npeers > 0) {
-    for (int q = 1; q < p.npeers; ++q) {   // peer order: deterministic
-      const double* ps = p.peers[q] + tile_off;
+    // peer order is fixed (deterministic); per fragment pair the loads of all peers are issued together, so the
+    // NVLink round trips overlap instead of queueing peer after peer
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
+    for (int t = 0; t < 8; ++t)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc[t][u][0] += ps[((t * 4 + u) * 2 + 0) * GTHREADS + tid];
-          acc[t][u][1] += ps[((t * 4 + u) * 2 + 1) * GTHREADS + tid];
+      for (int u = 0; u < 4; ++u) {
+        double v0[7], v1[7];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+          const bool on = q < p.npeers;
+          v0[q - 1] = on ? (p.peers[q] + tile_off)[((t * 4 + u) * 2 + 0) * GTHREADS + tid] : 0.0;
+          v1[q - 1] = on ? (p.peers[q] + tile_off)[((t * 4 + u) * 2 + 1) * GTHREADS + tid] : 0.0;
         }
-    }
+#pragma unroll
+        for (int q = 1; q < 8; ++q) { acc[t][u][0] += v0[q - 1]; acc[t][u][1] += v1[q - 1]; }
+      }
   } else {
     for (int s = 1; s < unit.nsplit; ++s) {
       const double* ps = src + s * split_stride;
@@ -511,13 +517,18 @@ __global__ void __launch_bounds__(256) k_partial_sum(const double* __restrict__ 
 
 // Statistics rows of a column-sharded evaluation: every rank holds its own column groups (zeros elsewhere) behind its
 // raw Grams in the symmetric buffer; out[i] = sum over peers, read over NVLink (replaces the second all-reduce).
+struct PeerList { const double* p[8]; };   // by value in the kernel parameters: no pointer table to upload
 template <typename T>
-__global__ void k_peer_sum_rows(const double* const* __restrict__ peers, int npeers, int64_t offset, int64_t n, T* __restrict__ out) {
+__global__ void k_peer_sum_rows(const PeerList peers, int npeers, int64_t offset, int64_t n, T* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double v = 0.0;
-  for (int q = 0; q < npeers; ++q) v += peers[q][offset + i];
-  out[i] = (T)v;
+  double v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = q < npeers ? peers.p[q][offset + i] : 0.0;   // all peer loads in flight together
+  double r = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) r += v[q];
+  out[i] = (T)r;
 }
 
 // CSR index normalisation: numpy wrap-around for negative indices, error flag for out-of-range ones.
