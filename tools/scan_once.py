@@ -1,3 +1,5 @@
+"""One column-sharded (8-way, then 1-way) statistics pass of cfg 2 with the binade scan forced on: the workload of the
+ncu captures in tools/final_evidence.sh (profiles/r01_scan_ncu_raw.csv, r01_launches_scan.csv)."""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
