@@ -479,7 +479,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
                  const void* w, int32_t mem, int64_t g0, int64_t g1, const FoldFuse* ff = nullptr) {
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
-  h->fitted = false;
+  h->fitted = false; h->filling = false;
   h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = w != nullptr;
   h->P = 0; h->csr_version++; h->plan = Plan();
   CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));

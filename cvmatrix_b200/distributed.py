@@ -1,6 +1,8 @@
 """
 Multi-GPU evaluation of fold batches: one process per GPU (torchrun), every rank holds a fitted CVMatrix on
-the same data, `torch.distributed` (NCCL over NVLink) carries the two small all-reduces of the row-sharded mode.
+the same data.  The row-sharded mode reduces over NVLink peer memory (symmetric memory: the fold owner sums its
+peers' raw Grams inside the epilogue kernel); `torch.distributed` (NCCL) carries the fallback all-reduce and the
+slab exchange of the sharded upload.
 See cvmatrix_b200/sharding.py for the sharding rules and include/cvmx.h (cvmx_sharded_*) for the device side.
 """
 
@@ -29,7 +31,8 @@ class ShardedFolds:
     ``training_batch`` returns device tensors for the folds THIS rank owns (a contiguous block, see
     ``sharding.fold_block``): dict(fold_begin, fold_end, XTX, XTY, stats, scal, status).  Many folds: each rank
     simply evaluates its block.  Few folds: every rank computes the raw Gram of its row shard of every fold and the
-    moment sums of its column groups; one all-reduce assembles both; each rank then finishes its own folds.
+    moment sums of its column groups; the owner of a fold sums its peers' buffers over NVLink inside the epilogue
+    kernel (or one NCCL all-reduce assembles them); each rank then finishes its own folds.
     """
 
     def __init__(self, cvm: CVMatrix, group=None):

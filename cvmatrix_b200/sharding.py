@@ -5,7 +5,8 @@ lets the N > 1 logic be tested on CPU with a gloo process group.
 
 The path shards two ways:
   * many folds  -> contiguous fold blocks per rank, no collective;
-  * few folds   -> every fold's rows are split across ranks (one all-reduce of the float64 Gram partials),
+  * few folds   -> every fold's rows are split across ranks (float64 Gram partials reduced by the fold owner over
+                   NVLink peer memory, or one all-reduce),
                    the sequential per-column moment chains are split by column group (one all-reduce of
                    the statistics rows, whose foreign entries are zero).
 """
