@@ -24,7 +24,7 @@
 //
 // The result is bit-identical to the sequential chain for every input (slow segments fall back to it; NaN / inf /
 // zero / cancelling sums are simply never fast).  tests/test_scan_model.py holds a numpy model of the same four
-// passes and its adversarial cases; tests/test_gpu_parity.py compares both kernels bit for bit.
+// passes and its adversarial cases; tests/test_gpu_scan.py compares the scan with the chains bit for bit.
 // Groups of 32 columns whose segments are mostly slow (e.g. mean-centred data: the sum wanders around zero) are
 // handed to k_moments_pipe instead (flag written by pass 2, read by passes 3 / 4 and by k_moments_pipe).
 #pragma once

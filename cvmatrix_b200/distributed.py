@@ -66,6 +66,31 @@ class ShardedFolds:
             status=t.empty((n_folds,), dtype=t.int32, device=self.dev),
         )
 
+    def _setup_symm(self, half_elems: int):
+        """Symmetric-memory buffer of 2 x half_elems float64 shared by all ranks of the group; returns None (on every rank)
+        unless every rank succeeded, so that all ranks take the same path."""
+        t, dist = self.torch, self.dist
+        ok, res = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty(2 * half_elems, dtype=t.float64, device=self.dev)
+            hdl = symm_mem.rendezvous(buf, grp)
+            ptrs = []
+            for half in range(2):
+                arr = (C.c_void_p * self.world)(*[int(p) + half * half_elems * 8 for p in hdl.buffer_ptrs])
+                ptrs.append(arr)
+            res = (buf, hdl, half_elems, ptrs)
+        except Exception:   # pragma: no cover - depends on the box (driver support for shareable allocations)
+            ok = 0
+        flag = t.tensor([ok], dtype=t.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.use_peers = False
+            return None
+        return res
+
     def training_batch(self, f0: int, f1: int, out: Optional[dict] = None, row_sharded: Optional[bool] = None):
         """Must be called on a non-default torch stream that the handle has been bound to (cvmx_set_stream), so
         that library kernels and NCCL collectives are ordered on one stream."""
@@ -118,35 +143,6 @@ class ShardedFolds:
         _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
                                            vp(out["scal"]), vp(out["status"])), h)
         return dict(out, fold_begin=o0, fold_end=o1)
-
-
-def _symm_setup(self, half_elems: int):
-    """Symmetric-memory buffer of 2 x half_elems float64 shared by all ranks of the group; returns None (on every rank)
-    unless every rank succeeded, so that all ranks take the same path."""
-    t, dist = self.torch, self.dist
-    ok, res = 1, None
-    try:
-        import torch.distributed._symmetric_memory as symm_mem
-
-        grp = self.group if self.group is not None else dist.group.WORLD
-        buf = symm_mem.empty(2 * half_elems, dtype=t.float64, device=self.dev)
-        hdl = symm_mem.rendezvous(buf, grp)
-        ptrs = []
-        for half in range(2):
-            arr = (C.c_void_p * self.world)(*[int(p) + half * half_elems * 8 for p in hdl.buffer_ptrs])
-            ptrs.append(arr)
-        res = (buf, hdl, half_elems, ptrs)
-    except Exception:   # pragma: no cover - depends on the box (driver support for shareable allocations)
-        ok = 0
-    flag = t.tensor([ok], dtype=t.int32, device=self.dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-    if int(flag.item()) == 0:
-        self.use_peers = False
-        return None
-    return res
-
-
-ShardedFolds._setup_symm = _symm_setup
 
 
 def fit_row_sharded(cvm: CVMatrix, X, Y=None, weights=None, group=None) -> None:
