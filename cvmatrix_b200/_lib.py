@@ -44,6 +44,7 @@ SIGNATURES = {
     "cvmx_sharded_gram": (_i32, [_vp, _i64, _i64, _u32, _i32, _i32, _vp]),
     "cvmx_sharded_finish": (_i32, [_vp, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvmx_sharded_finish_peers": (_i32, [_vp, _i64, _i64, _i64, _i64, _u32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "cvmx_validation_rows": (_i32, [_vp, _i64, _vp, _u32, _vp, _vp, _i32]),
     "cvmx_profile_enable": (_i32, [_vp, _i32]),
     "cvmx_profile_read": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cvmx_partition_labels": (_i64, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

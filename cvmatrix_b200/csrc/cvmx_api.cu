@@ -999,6 +999,51 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   return CVMX_OK;
 }
 
+
+template <typename T>
+int32_t validation_rows_impl(cvmx_t* h, int64_t fold, const void* stats, uint32_t apply, void* out_X, void* out_Y, int32_t mem) {
+  const size_t sz = sizeof(T);
+  const int64_t K = h->K, M = h->M, ld = h->ld, C = K + M;
+  const int64_t beg = h->h_off[fold], n = h->h_off[fold + 1] - beg;
+  if (n == 0) return CVMX_OK;
+  const T* dstats = nullptr;       // [2][C]: mean row, std row
+  if (stats && apply) {
+    if (mem == CVMX_HOST) {
+      CU(h, h->out_small.reserve(2 * C * sz));
+      CU(h, cudaMemcpyAsync(h->out_small.p, stats, 2 * C * sz, cudaMemcpyHostToDevice, h->stream));
+      dstats = h->out_small.as<T>();
+    } else {
+      dstats = (const T*)stats;
+    }
+  }
+  // the kernel indexes mean / std by absolute column of [X | Y]
+  const T* mean = dstats, *sdev = dstats ? dstats + C : nullptr;
+  const int64_t* idx = h->d_idx.as<int64_t>() + beg;
+  T* dX = (T*)out_X; T* dY = (T*)out_Y;
+  if (mem == CVMX_HOST) {
+    if (out_X) { CU(h, h->out_xx.reserve((size_t)n * K * sz)); dX = h->out_xx.as<T>(); }
+    if (out_Y && M) { CU(h, h->out_xy.reserve((size_t)n * M * sz)); dY = h->out_xy.as<T>(); }
+  }
+  const unsigned grid = (unsigned)(h->sm_count * 8);
+  if (out_X) {
+    k_validation_rows<T><<<grid, 256, 0, h->stream>>>(h->Z.as<T>(), ld, idx, n, 0, K, (apply & CVMX_CENTER_X) ? mean : nullptr,
+                                                      (apply & CVMX_SCALE_X) ? sdev : nullptr, dX);
+    h->launches++;
+  }
+  if (out_Y && M) {
+    k_validation_rows<T><<<grid, 256, 0, h->stream>>>(h->Z.as<T>(), ld, idx, n, K, M, (apply & CVMX_CENTER_Y) ? mean : nullptr,
+                                                      (apply & CVMX_SCALE_Y) ? sdev : nullptr, dY);
+    h->launches++;
+  }
+  CU(h, cudaGetLastError());
+  if (mem == CVMX_HOST) {
+    if (out_X) CU(h, cudaMemcpyAsync(out_X, dX, (size_t)n * K * sz, cudaMemcpyDeviceToHost, h->stream));
+    if (out_Y && M) CU(h, cudaMemcpyAsync(out_Y, dY, (size_t)n * M * sz, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return CVMX_OK;
+}
+
 int32_t upload_tables(cvmx_t* h, TableCache& tc, const std::vector<int64_t>& key, const Plan& pl) {
   CU(h, tc.units.reserve(std::max<size_t>(1, pl.units.size()) * sizeof(GramUnit)));
   CU(h, tc.tiles.reserve(std::max<size_t>(1, pl.tiles.size()) * sizeof(int2)));
@@ -1584,6 +1629,16 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
     CU(h, cudaGetLastError());
   }
   return CVMX_OK;
+}
+
+
+int32_t cvmx_validation_rows(cvmx_t* h, int64_t fold, const void* stats, uint32_t apply, void* out_X, void* out_Y, int32_t mem) {
+  if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: fit first");
+  if (fold < 0 || fold >= h->P) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: fold outside the CSR");
+  if (apply && !stats) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: statistics needed for centring / scaling");
+  CU(h, cudaSetDevice(h->device));
+  return h->dtype == CVMX_F64 ? validation_rows_impl<double>(h, fold, stats, apply, out_X, out_Y, mem)
+                              : validation_rows_impl<float>(h, fold, stats, apply, out_X, out_Y, mem);
 }
 
 int32_t cvmx_profile_enable(cvmx_t* h, int32_t on) {

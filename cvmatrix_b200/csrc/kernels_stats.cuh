@@ -462,6 +462,22 @@ constexpr size_t moments_pipe_smem(int stages) {
 }
 constexpr int MOM_STAGES_DEEP = 8;      // few long chains: ~140 KB of gathered rows in flight per CTA
 
+// Validation rows of a fold for the caller's next step (prediction on the held-out rows): out[i][c] = Z[idx[i]][c0 + c],
+// optionally (z - mean) / std with the training-set statistics, each op individually rounded like numpy's
+// (X[val] - X_mean) / X_std.
+template <typename T>
+__global__ void k_validation_rows(const T* __restrict__ Z, int64_t ld, const int64_t* __restrict__ idx, int64_t n, int64_t c0,
+                                  int64_t ncols, const T* __restrict__ mean, const T* __restrict__ sdev, T* __restrict__ out) {
+  const int64_t total = n * ncols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ncols, c = e - r * ncols;
+    T v = Z[idx[r] * ld + c0 + c];
+    if (mean) v = Rn<T>::sub(v, mean[c0 + c]);
+    if (sdev) v = Rn<T>::div(v, sdev[c0 + c]);
+    out[e] = v;
+  }
+}
+
 // mean / std of every (fold, column) from the raw fold sums (deferred finalisation, see MomentParams::raw)
 template <typename T>
 __global__ void k_finalize_stats(MomentParams<T> p, int64_t nfolds) {

@@ -191,6 +191,7 @@ class CVMatrix:
         if self.weights is not None and self.weights.shape[0] != self.N:
             raise ValueError("weights must have one entry per row of X")
         self._partitioner = None
+        self._n_folds = 0
 
         Xd, ldx = self._rows(self.X)
         Yd, ldy = self._rows(self.Y) if self.Y is not None else (None, 0)
@@ -207,6 +208,7 @@ class CVMatrix:
             _lib.check(rc, self._h)
             self._partitioner = folds
             self._n_folds = offsets.size - 1
+            self._offsets = offsets
         else:
             rc = self._lib.cvmx_fit(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST, g0, g1)
             _lib.check(rc, self._h)
@@ -416,6 +418,7 @@ class CVMatrix:
         rc = self._lib.cvmx_set_folds(self._h, _ptr(offsets), _ptr(indices), offsets.size - 1, _lib.HOST)
         _lib.check(rc, self._h)
         self._n_folds = offsets.size - 1
+        self._offsets = offsets
 
     def training_batch(self, fold_begin: int = 0, fold_end: Optional[int] = None, return_XTX: bool = True,
                        return_XTY: bool = True, out: str = "numpy", check: bool = True):
@@ -498,6 +501,48 @@ class CVMatrix:
             Y_mean=mean[:, :, K:] if need[2] else None, Y_std=std[:, :, K:] if need[3] else None,
             sum_w_train=scal[:, 0], nnz_train=scal[:, 1], status=status,
         )
+
+    def validation_rows(self, fold: int, stats: Optional[Stats] = None, out: str = "numpy"):
+        """
+        ``(X[val], Y[val])`` of CSR fold number ``fold`` (see ``set_folds``) for the caller's next step - predicting the
+        held-out rows.  With ``stats`` = ``(X_mean, X_std, Y_mean, Y_std)`` as returned by ``training_*`` for that fold,
+        every entry that is not None is applied: ``(X[val] - X_mean) / X_std`` and likewise for Y, bit-identical to
+        the numpy expressions.  ``out="torch"`` returns CUDA tensors (the rows never leave the device).
+        """
+        self._require_fit()
+        if not 0 <= fold < getattr(self, "_n_folds", 0):
+            raise ValueError(f"Fold {fold} not found.")
+        K, M, dt = self.K, self.M or 0, self.dtype
+        offsets = self._offsets
+        n = int(offsets[fold + 1] - offsets[fold])
+        apply, packed = 0, None
+        if stats is not None:
+            packed = np.zeros((2, K + M), dt)
+            for row, lo, hi, bit, s in ((0, 0, K, 1, stats[0]), (1, 0, K, 4, stats[1]), (0, K, K + M, 2, stats[2]), (1, K, K + M, 8, stats[3])):
+                if s is not None and hi > lo:
+                    packed[row, lo:hi] = np.asarray(s, dtype=dt).reshape(-1)
+                    apply |= bit
+        if out == "torch":
+            import torch
+
+            tdt = torch.float64 if np.dtype(dt) == np.float64 else torch.float32
+            dev = torch.device("cuda", self.device)
+            Xv = torch.empty((n, K), dtype=tdt, device=dev)
+            Yv = torch.empty((n, M), dtype=tdt, device=dev) if M else None
+            st = torch.from_numpy(packed).to(dev) if apply else None
+            torch.cuda.current_stream(dev).synchronize()
+            p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+            rc = self._lib.cvmx_validation_rows(self._h, fold, p(st), apply, p(Xv), p(Yv), _lib.DEVICE)
+            _lib.check(rc, self._h)
+            self.sync()
+            return Xv, Yv
+        if out != "numpy":
+            raise ValueError("out must be 'numpy' or 'torch'")
+        Xv = np.empty((n, K), dt)
+        Yv = np.empty((n, M), dt) if M else None
+        rc = self._lib.cvmx_validation_rows(self._h, fold, _ptr(packed) if apply else None, apply, _ptr(Xv), _ptr(Yv), _lib.HOST)
+        _lib.check(rc, self._h)
+        return Xv, Yv
 
     def _pinned(self, name: str, shape, dtype=None) -> np.ndarray:
         import torch

@@ -207,6 +207,15 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
                                   const void* const* peer_bufs, int32_t n_peers, int64_t gram_count, void* out_XTX,
                                   void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status);
 
+/* The validation rows of CSR fold `fold` for the caller's next step (predicting the held-out rows with a model built
+ * from the training matrices - what ikpls does after training_XTX_XTY, cvmatrix/partitioner.py:27-31): out_X [n_val, K]
+ * = X[val], out_Y [n_val, M] = Y[val] (either may be NULL), optionally centred / scaled with training-set statistics:
+ * `stats` is [2][K+M] (mean row, std row: the out_stats layout of cvmx_training_batch) in `mem`, `apply` a mask of
+ * CVMX_CENTER_X | CVMX_CENTER_Y | CVMX_SCALE_X | CVMX_SCALE_Y; each op is individually rounded, so the result equals
+ * numpy's (X[val] - X_mean) / X_std bit for bit.  `mem` applies to stats and to both outputs. */
+int32_t cvmx_validation_rows(cvmx_t* h, int64_t fold, const void* stats, uint32_t apply, void* out_X, void* out_Y,
+                             int32_t mem);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, CUDA events are recorded on the
  * handle's stream around the statistics kernels (ms[0]), the Gram kernel (ms[1]) and the split-reduce
  * kernel (ms[2]); cvmx_profile_read synchronises, returns the accumulated milliseconds and span counts
