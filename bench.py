@@ -2,16 +2,19 @@
 """
 bench.py - fold matrices / second of the cvmatrix hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg3|cfg4] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg3|cfg4|cfg5s] [--impl native|reference]
 
 One "step" = one pass of the batched fold path (cvmx_training_batch: weight masses, numpy-order
 moments, DMMA Gram downdate, fused centering/scaling epilogue) over ALL folds of the workload, inputs
 resident in HBM, outputs written to HBM.  `value` = folds processed by all ranks / max-over-ranks device
 time.  `e2e` = the reference benchmark's own definition (benchmarks/benchmark.py:52-158): Partitioner +
 fit (host->device copy of X, Y, w from pinned memory) + all folds + device->host copy of every result,
-through the public CVMatrix API.  `cpu_baseline` / `--impl reference` time the numpy restatement of the
-reference (oracle/cvmatrix_oracle.py, order="numpy": the same numpy calls the reference makes) on the
-box's host cores.
+through the public CVMatrix API.  `cpu_baseline` / `--impl reference` time the reference itself - the
+unmodified package staged in oracle/_ref by `make -C oracle ref` (kind "reference"), else the pinned numpy
+restatement oracle/cvmatrix_oracle.py (kind "port") - on the box's host cores, all BLAS threads.
+`parity` compares the timed path's results with that reference on the same inputs (relative Frobenius error
+of XTX, XTY and the joint [XTX | XTY]; statistics bit for bit), `also` carries device-timed lines of the other
+two single-GPU workloads (cfg3, cfg4) measured in the same process.
 
 Workloads (BASELINE.json configs; inputs per benchmarks/benchmark.py:223-232, seed 42, uniform [0,1)):
   cfg2  N=1,000,000 K=500 M=10 float64 weighted center+scale, 5 folds      (default; metric config)
@@ -22,16 +25,32 @@ Inputs (4.09 GB) are far larger than the 126 MB L2, so consecutive steps cannot 
 
 from __future__ import annotations
 
-import argparse
-import ctypes as C
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+
+def _host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+# The CPU reference must get every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+# starve OpenBLAS on rank 0 (the only rank that runs the reference).  Fixed before numpy loads its BLAS.
+if int(os.environ.get("RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(_v, "") in ("", "1"):
+            os.environ[_v] = str(_host_cores())
+
+import argparse  # noqa: E402
+import ctypes as C  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -43,6 +62,7 @@ CONFIGS = {
     # contract self-test shape (tests/test_bench_contract.py)
     "tiny": dict(N=4_000, K=24, M=3, P=4, name="self-test: N=4k K=24 M=3 f64 4-fold"),
     # cfg 5 (wide, K=5000 M=100) at reduced N: the full N=2M matrix is 80 GB and cannot be generated on the host
+    # (full size: tools/bench_cfg5.py on one GPU, tools/bench_cfg5_sharded.py row-sharded over N GPUs)
     "cfg5s": dict(N=100_000, K=5000, M=100, P=10, name="wide K=5000 M=100 f64 weighted center+scale 10-fold at N=100k (cfg 5 scaled to 1/20 of its rows)"),
     # reduced shapes for ncu captures only (same per-CTA work as cfg2 / cfg3 / cfg4, fewer CTAs)
     "prof2": dict(N=200_000, K=500, M=10, P=5, name="profiling: N=200k K=500 M=10 f64 5-fold"),
@@ -51,6 +71,7 @@ CONFIGS = {
 }
 METRIC = "fold matrices/sec"
 UNIT = "fold-matrices/s"
+REF_BUDGET_S = 150.0   # wall-clock budget of the reference arm's warm-up + timed steps
 
 
 def fp64_peak_tflops():
@@ -94,6 +115,21 @@ def make_host_inputs(cfg, pinned):
     return X, Y, w, folds, keep
 
 
+def row_sharded_mode(P, world):
+    return world > 1 and P < 4 * world          # cvmatrix_b200.sharding.use_row_sharding
+
+
+def config_dict(cfg, world):
+    """The `config` object of the JSON line - identical for the native and the reference arm."""
+    N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
+    par = (f"rows of each fold sharded x{world}, fold owners reduce over NVLink peer memory" if row_sharded_mode(P, world)
+           else f"fold-sharded x{world}")
+    return {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": par,
+            "l2_policy": ("inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8
+                          else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2"),
+            "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -130,69 +166,222 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CPU reference (checker / baseline only)
+# ---------------------------------------------------------------------------------------------------------------
+def load_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_loader
+
+    threads = reference_loader.use_all_host_threads()
+    RefCV, RefPart, kind = reference_loader.load()
+    return RefCV, RefPart, kind, threads, reference_loader.blas_threads()
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a - b))
+
+
+def parity_entry(got, ref):
+    """got / ref: (XTX, XTY, (X_mean, X_std, Y_mean, Y_std)) of one fold."""
+    XTX, XTY, st = got
+    rXTX, rXTY, rst = ref
+    exact = all((a is None and b is None) or (a is not None and b is not None and np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)))
+                for a, b in zip(st, rst))
+    return {"xtx": rel_fro(XTX, rXTX), "xty": rel_fro(XTY, rXTY),
+            "joint": rel_fro(np.hstack([XTX, XTY]), np.hstack([rXTX, rXTY])), "stats_bit_exact": bool(exact)}
+
+
+def parity_summary(entries, kind, what):
+    if not entries:
+        return None
+    return {"xtx": max(e["xtx"] for e in entries), "xty": max(e["xty"] for e in entries), "joint": max(e["joint"] for e in entries),
+            "stats_bit_exact": all(e["stats_bit_exact"] for e in entries), "folds_checked": len(entries),
+            "against": f"{kind} (numpy backend) on the same inputs", "what": what,
+            "tolerance": "north_star: relFro <= 1e-12 (float64); centred XTY alone at N = 1M has a ~3-4e-12 floor against OpenBLAS for "
+                         "any independent summation order (SURVEY.md Appendix B), XTX and the joint matrix do not"}
+
+
 def run_reference(args, cfg, rank, world):
-    """Reference arm: the reference's CPU path (numpy restatement, all host threads) on a bounded row sample of
-    the same workload; one step = Partitioner + fit + every fold, as benchmarks/benchmark.py times it."""
+    """Reference arm: the reference's own CPU implementation at FULL size, all host threads; one step =
+    Partitioner + fit + every fold (training_XTX_XTY), exactly what benchmarks/benchmark.py:52-158 times.  The
+    number of timed steps is clamped so that warm-up + steps fit REF_BUDGET_S; the clamped numbers are printed."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from cvmatrix_oracle import OracleCVMatrix, OraclePartitioner
-
+    RefCV, RefPart, kind, threads, blas = load_reference()
     N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
     X, Y, w, folds, _ = make_host_inputs(cfg, pinned=False)
+    loo = P > 1000
+    # leave-one-out at full size is ~90 s per pass: time the full fit and a fixed sample of folds per step
+    n_folds = P if not loo else 2000
 
-    def one_step(n_rows, n_folds):
+    def one_step():
         t0 = time.perf_counter()
-        part = OraclePartitioner(folds[:n_rows])
-        m = OracleCVMatrix(dtype=np.float64, copy=False, order="numpy")
-        m.fit(X[:n_rows], Y[:n_rows], w[:n_rows])
+        part = RefPart(folds)
+        m = RefCV(dtype=np.float64, copy=False)
+        m.fit(X, Y, w)
         t1 = time.perf_counter()
         for f in list(part.folds_dict)[:n_folds]:
             m.training_XTX_XTY(part.get_validation_indices(f))
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
 
-    # calibrate on a small slice, then size the sample so the whole run stays within ~3 minutes
-    n_cal = min(N, 50_000 if P <= 1000 else N)
-    f_cal = min(P, 50)
-    fit_s, fold_s = one_step(n_cal, f_cal)
-    est_full = fit_s * N / n_cal + (fold_s / f_cal) * P * (N / n_cal if P <= 1000 else 1.0)
-    budget = 170.0 / max(1, args.steps + args.warmup)
-    if P <= 1000:  # large folds: sample rows (cost is linear in N), keep every fold
-        frac = min(1.0, budget / est_full)
-        n_rows = max(P * 20, int(N * frac) // P * P)
-        n_folds, scale = P, N / n_rows
-    else:          # leave-one-out: full fit, sample folds (cost is linear in the number of folds)
-        n_rows = N
-        n_folds = int(max(50, min(P, (budget - fit_s) / max(fold_s / f_cal, 1e-9))))
-        scale = None
-    for _ in range(args.warmup):
-        one_step(n_rows, n_folds)
+    t_begin = time.perf_counter()
+    first = one_step()                      # warm-up step 1 (also the calibration of the clamp)
+    est = sum(first)
+    warmup = 1
+    while warmup < args.warmup and (time.perf_counter() - t_begin) + est * 2 < REF_BUDGET_S * 0.4:
+        one_step()
+        warmup += 1
+    left = REF_BUDGET_S - (time.perf_counter() - t_begin)
+    steps = int(max(1, min(args.steps, left // est)))
     t_fit = t_fold = 0.0
-    for _ in range(args.steps):
-        a, b = one_step(n_rows, n_folds)
+    for _ in range(steps):
+        a, b = one_step()
         t_fit += a
         t_fold += b
-    t_fit /= args.steps
-    t_fold /= args.steps
-    if scale is not None:
-        step_s = (t_fit + t_fold) * scale
-        sample = f"first {n_rows} of {N} rows, all {P} folds, time scaled linearly by {scale:.2f}"
-    else:
-        step_s = t_fit + t_fold * (P / n_folds)
-        sample = f"full fit, first {n_folds} of {P} folds, fold time scaled by {P / n_folds:.1f}"
+    t_fit /= steps
+    t_fold /= steps
+    scale = P / n_folds
+    step_s = t_fit + t_fold * scale
+    sample = ("full size: every row, every fold" if not loo else
+              f"full-size fit, first {n_folds} of {P} folds per step, fold time scaled by {scale:.1f}")
     value = P / step_s
-    cores = os.cpu_count()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "step": "Partitioner + fit + all folds (training_XTX_XTY), host arrays, copy=False"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "fit_s_sample": t_fit, "folds_s_sample": t_fold},
+        "config": config_dict(cfg, world),
+        "reference_step": "Partitioner + fit + all folds (training_XTX_XTY), host arrays in, host arrays out, copy=False "
+                          "(benchmarks/benchmark.py:52-158); runs on rank 0's host cores only",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "blas_threads": blas, "kind": kind, "sample": sample,
+                         "fit_s": t_fit, "folds_s": t_fold * scale, "fold_path_value": P / (t_fold * scale)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def alloc_outputs(ctx, n, K, M):
+    t = ctx.torch
+    return dict(XTX=t.empty((n, K, K), dtype=t.float64, device=ctx.dev), XTY=t.empty((n, K, M), dtype=t.float64, device=ctx.dev),
+                stats=t.empty((n, 2, K + M), dtype=t.float64, device=ctx.dev), scal=t.empty((n, 2), dtype=t.float64, device=ctx.dev),
+                status=t.empty((n,), dtype=t.int32, device=ctx.dev))
+
+
+def time_fold_path(ctx, m, P, steps, warmup, sf=None, row_sharded=False, clocks=False):
+    """Device-timed fold path over all P folds of m's CSR: max over ranks of the CUDA-event time per step."""
+    from cvmatrix_b200 import _lib
+
+    torch, lib, h = ctx.torch, m._lib, m._h
+    K, M = m.K, m.M or 0
+    f0, f1 = (0, P) if row_sharded else (ctx.rank * P // ctx.world, (ctx.rank + 1) * P // ctx.world)
+    # LOO writes 2.04 MB per fold: keep the resident output window bounded (it is rewritten every chunk)
+    chunk = min(max(f1 - f0, 1), 4096) if not row_sharded else P
+    outs = alloc_outputs(ctx, chunk, K, M)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.cvmx_set_stream(h, C.c_void_p(ctx.stream.cuda_stream)), h)
+
+    def step():
+        if row_sharded:
+            sf.training_batch(0, P, out=outs, row_sharded=True)
+            return
+        for c0 in range(f0, f1, chunk):
+            c1 = min(f1, c0 + chunk)
+            _lib.check(lib.cvmx_training_batch(h, c0, c1, 3, vp(outs["XTX"]), vp(outs["XTY"]), vp(outs["stats"]), vp(outs["scal"]),
+                                               vp(outs["status"]), _lib.DEVICE), h)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    _lib.check(lib.cvmx_profile_enable(h, 1), h)
+    launches0 = m.launch_count
+    sampler = ClockSampler(ctx.local_rank) if (clocks and ctx.rank == 0) else None
+    if sampler:
+        sampler.start()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ctx.stream)
+    for _ in range(steps):
+        step()
+    e1.record(ctx.stream)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = sampler.stop() if sampler else None
+    launches = m.launch_count - launches0
+    prof_ms, prof_n = (C.c_double * 3)(), (C.c_int64 * 3)()
+    _lib.check(lib.cvmx_profile_read(h, prof_ms, prof_n), h)
+    _lib.check(lib.cvmx_profile_enable(h, 0), h)
+    if ctx.world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=ctx.dev)
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return dict(ms_per_step=ms / steps, prof_ms=[v / steps for v in prof_ms], prof_n=[v / steps for v in prof_n],
+                launches=int(launches), clocks=clk, outs=outs, fold_range=(f0, f1), chunk=chunk)
+
+
+def roofline_of(cfg_name, cfg, world, rank_rows, rank_folds, timing, ms_per_step):
+    """Roofline of the dominant kernel on THIS rank: rank_rows validation rows contracted and rank_folds results
+    written per step (flops = 2 N_val K (K+M) per fold, bytes = 2 s K (K+M) per fold)."""
+    K, M = cfg["K"], cfg["M"]
+    flops = 2.0 * rank_rows * K * (K + M)
+    nbytes = 2.0 * 8 * K * (K + M) * rank_folds
+    gram_ms, gram_n = timing["prof_ms"][1], timing["prof_n"][1]
+    peak_tf, peak_src = fp64_peak_tflops()
+    peak_bw, bw_src = hbm_peak_gbs()
+    t_flop, t_byte = flops / (peak_tf * 1e12), nbytes / (peak_bw * 1e9)
+    if t_flop >= t_byte:
+        ach = flops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if ach else None,
+                "peak_source": peak_src + "; FP64 tensor pipe", "kernel": "k_gram<double>"}
+        if ach:
+            # flops the kernel actually issues: tiles on / above the diagonal only, diagonal tiles at 3/4 (DESIGN.md 5.1)
+            TI, TJ = -(-K // 128), -(-(K + M) // 128)
+            issued_tiles = sum((0.75 if bj == bi else 1.0) for bi in range(TI) for bj in range(bi, TJ))
+            issued = 2.0 * rank_rows * 128 * 128 * issued_tiles
+            roof["issued_flops_per_step"] = issued
+            roof["issued_frac_of_peak"] = issued / (gram_ms * 1e-3) / 1e12 / peak_tf
+            roof["note"] = ("achieved / frac use the FULL flop count 2 N_val K (K+M) of SURVEY.md 8(d); XTX is symmetric, so only "
+                            "upper-triangular tiles are computed and frac can exceed 1 - issued_frac_of_peak is the DMMA pipe's own load")
+    else:
+        ach = nbytes / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else None
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw if ach else None,
+                "peak_source": bw_src, "kernel": "k_loo_operands + k_loo_tiles<double>",
+                "note": "algorithmic bytes = read the resident total + write the result per fold (SURVEY.md 8(d)); the totals stay "
+                        "in registers, so what reaches DRAM is the write half: write_gbs is achieved / 2",
+                "write_gbs": ach / 2 if ach else None}
+    roof.update({"traffic": None, "kernel_ms_per_step": gram_ms, "kernel_launches_per_step": gram_n,
+                 "stats_ms_per_step": timing["prof_ms"][0], "reduce_ms_per_step": timing["prof_ms"][2],
+                 "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": nbytes, "per": "rank 0" if world > 1 else "GPU",
+                 "step_roofline_frac": max(t_flop, t_byte) / (ms_per_step * 1e-3)})
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        roof["traffic"] = tj.get(cfg_name if world == 1 else f"{cfg_name}@{world}")   # ncu capture of the same per-rank launch
+    except Exception:
+        pass
+    return roof
+
+
+def native_fold_results(m, folds_idx, K):
+    """Host copies of the batched path's results for the given CSR fold numbers (XTX, XTY, 4 statistics rows)."""
+    res = {}
+    for f in folds_idx:
+        r = m.training_batch(f, f + 1, out="numpy")
+        res[f] = (r["XTX"][0], r["XTY"][0], (r["X_mean"][0], r["X_std"][0], r["Y_mean"][0], r["Y_std"][0]))
+    return res
 
 
 def main():
@@ -204,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the cfg3 / cfg4 lines appended to the default (cfg2) run")
+    ap.add_argument("--no-parity", action="store_true", help="skip the comparison with the CPU reference (N > 1: one fold on rank 0)")
     ap.add_argument("--e2e-out", default="numpy", choices=["numpy", "pinned"],
                     help="host destination of the e2e results: fresh numpy arrays (the reference's convention) or the reused page-locked pool")
     args = ap.parse_args()
@@ -220,20 +411,24 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from cvmatrix_b200 import CVMatrix, Partitioner, _lib
+    from cvmatrix_b200 import CVMatrix, Partitioner, _lib, sharding
+    from cvmatrix_b200.distributed import ShardedFolds, fit_sharded_upload
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION / INFO print to stdout; the contract is ONE JSON line there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: NCCL's own log (NCCL_DEBUG=INFO / VERSION) goes to stderr unless the caller
+        # already pointed it at a file
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world, ctx.local_rank = torch, dist, dev, rank, world, local_rank
+    ctx.barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    ctx.stream = torch.cuda.Stream(dev)   # a real (non-default) stream shared by the library and the timing events
+    torch.cuda.set_stream(ctx.stream)
 
     N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
     X, Y, w, folds, keep = make_host_inputs(cfg, pinned=True)
@@ -244,119 +439,94 @@ def main():
     m.fit(X, Y, w)
     fit_upload_s = time.perf_counter() - t0
     m.set_folds(part)
-    # folds are sharded across ranks in contiguous blocks; no data-path collective
-    f0, f1 = rank * P // world, (rank + 1) * P // world
-    Pl = f1 - f0
-    # LOO writes 2.04 MB per fold: keep the resident output window bounded (it is rewritten every chunk)
-    chunk = min(max(Pl, 1), 4096)
-    oxx = torch.empty((chunk, K, K), dtype=torch.float64, device=dev)
-    oxy = torch.empty((chunk, K, M), dtype=torch.float64, device=dev)
-    ost = torch.empty((chunk, 2, K + M), dtype=torch.float64, device=dev)
-    osc = torch.empty((chunk, 2), dtype=torch.float64, device=dev)
-    oss = torch.empty((chunk,), dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(dev)   # a real (non-default) stream shared by the library and the timing events
-    torch.cuda.set_stream(stream)
-    _lib.check(lib.cvmx_set_stream(h, C.c_void_p(stream.cuda_stream)), h)
-    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-
-    from cvmatrix_b200 import sharding
-    from cvmatrix_b200.distributed import ShardedFolds
 
     row_sharded = sharding.use_row_sharding(P, world)
+    assert row_sharded == row_sharded_mode(P, world)
     sf = ShardedFolds(m) if world > 1 else None
     emulate = int(os.environ.get("BENCH_EMULATE_SHARDS", "0"))   # profiling aid: rank 0's share of an N-way sharded step
     if emulate and world == 1:
         sf = ShardedFolds(m)
         sf.emulate_shards = emulate
         row_sharded = True
-    outs = dict(XTX=oxx, XTY=oxy, stats=ost, scal=osc, status=oss)
 
-    def step():
-        if row_sharded:
-            # few large folds: rows of every fold split across ranks, 1 NCCL all-reduce, owners finish their folds
-            sf.training_batch(0, P, out=outs, row_sharded=True)
-            return
-        for c0 in range(f0, f1, chunk):
-            c1 = min(f1, c0 + chunk)
-            _lib.check(lib.cvmx_training_batch(h, c0, c1, 3, vp(oxx), vp(oxy), vp(ost), vp(osc), vp(oss), _lib.DEVICE), h)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    _lib.check(lib.cvmx_profile_enable(h, 1), h)
-    launches0 = m.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = m.launch_count - launches0
-    prof_ms = (C.c_double * 3)()
-    prof_n = (C.c_int64 * 3)()
-    _lib.check(lib.cvmx_profile_read(h, prof_ms, prof_n), h)
-    _lib.check(lib.cvmx_profile_enable(h, 0), h)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+    # ---- the timed region: fold path, inputs resident -------------------------------------------------------
+    tm = time_fold_path(ctx, m, P, args.steps, args.warmup, sf=sf, row_sharded=row_sharded, clocks=True)
+    ms_per_step = tm["ms_per_step"]
     value = P / (ms_per_step * 1e-3)
-
-    # ---- roofline of the dominant kernel (k_gram: DMMA Gram + fused epilogue) on this rank ---------------
-    n_val_total = int(part.offsets[f1] - part.offsets[f0]) if not row_sharded else int(part.offsets[P]) // world
-    flops_per_step = 2.0 * n_val_total * K * (K + M)             # full (no symmetry credit), SURVEY.md 8(d)
-    bytes_per_step = 2.0 * 8 * K * (K + M) * Pl                  # read total + write result per fold
-    gram_ms = prof_ms[1] / max(1, args.steps)                    # all k_gram launches of one step
-    gram_launches = prof_n[1] / max(1, args.steps)
-    peak_tf, peak_src = fp64_peak_tflops()
-    peak_bw, bw_src = hbm_peak_gbs()
-    t_flop, t_byte = flops_per_step / (peak_tf * 1e12), bytes_per_step / (peak_bw * 1e9)
-    if t_flop >= t_byte:
-        ach = flops_per_step / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if ach else None,
-                "peak_source": peak_src + "; FP64 tensor pipe"}
+    f0, f1 = tm["fold_range"]
+    shards = emulate or world
+    if row_sharded:
+        rank_rows, rank_folds = int(part.offsets[P]) // shards, P / shards
     else:
-        ach = bytes_per_step / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else None
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw if ach else None,
-                "peak_source": bw_src}
-    if roof["bound"] == "tensor" and ach:
-        # flops the kernel actually issues: tiles on / above the diagonal only, diagonal tiles at 3/4
-        TI, TJ = -(-K // 128), -(-(K + M) // 128)
-        issued_tiles = sum((0.75 if bj == bi else 1.0) for bi in range(TI) for bj in range(bi, TJ))
-        issued = 2.0 * n_val_total * 128 * 128 * issued_tiles
-        roof["issued_flops_per_step"] = issued
-        roof["issued_frac_of_peak"] = issued / (gram_ms * 1e-3) / 1e12 / peak_tf
-        roof["note"] = ("achieved / frac use the FULL flop count 2 N_val K (K+M) of SURVEY.md 8(d); XTX is symmetric, so only "
-                        "upper-triangular tiles are computed and frac can exceed 1 - issued_frac_of_peak is the DMMA pipe's own load")
-    roof.update({"kernel": "k_gram<double>", "traffic": None, "kernel_ms_per_step": gram_ms, "kernel_launches_per_step": gram_launches,
-                 "stats_ms_per_step": prof_ms[0] / max(1, args.steps), "reduce_ms_per_step": prof_ms[2] / max(1, args.steps),
-                 "algorithmic_flops_per_step": flops_per_step, "algorithmic_bytes_per_step": bytes_per_step,
-                 "step_roofline_frac": max(t_flop, t_byte) / (ms_per_step * 1e-3)})
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roof["traffic"] = json.load(f).get(args.config)
-    except Exception:
-        pass
+        rank_rows, rank_folds = int(part.offsets[f1] - part.offsets[f0]), f1 - f0
+    roof = roofline_of(args.config, cfg, world, rank_rows, rank_folds, tm, ms_per_step)
+    outs, clocks, launches = tm["outs"], tm["clocks"], tm["launches"]
+
+    # results of the timed path for the parity block (before e2e refits the handle)
+    want_parity = not args.no_parity and not emulate
+    native_res, owner_of = {}, {}
+    if want_parity:
+        if world == 1:
+            if not args.no_cpu_baseline:
+                native_res = native_fold_results(m, list(range(min(P, 5))) if P <= 1000 else [0, 1, P // 2, P - 1], K)
+        elif row_sharded:
+            # fold 0 of the row-sharded step, fetched from its owner (rank 0 may own no fold)
+            o = [sharding.fold_block(r, world, 0, P) for r in range(world)]
+            src = next(r for r, (a, b) in enumerate(o) if a <= 0 < b)
+            torch.cuda.synchronize()
+            bufs = [outs["XTX"][:1].clone(), outs["XTY"][:1].clone(), outs["stats"][:1].clone()]   # owner: its fold 0 sits first
+            for b in bufs:
+                dist.broadcast(b, src=src)
+            if rank == 0:
+                st = bufs[2][0].cpu().numpy()
+                native_res[0] = (bufs[0][0].cpu().numpy(), bufs[1][0].cpu().numpy(), (st[0, :K], st[1, :K], st[0, K:], st[1, K:]))
+        else:
+            torch.cuda.synchronize()
+            if rank == 0:     # first fold of rank 0's own block
+                lo = f0 + ((f1 - f0 - 1) // tm["chunk"]) * tm["chunk"]   # the chunk that is still in the output window
+                st = outs["stats"][0].cpu().numpy()
+                native_res[lo] = (outs["XTX"][0].cpu().numpy(), outs["XTY"][0].cpu().numpy(), (st[0, :K], st[1, :K], st[0, K:], st[1, K:]))
+
+    # ---- the other single-box workloads, device-timed in the same process (default run only) -----------------
+    also = None
+    if args.config == "cfg2" and not args.no_also and not emulate:
+        also = {}
+        a_steps, a_warm = max(3, min(args.steps, 8)), 3
+        c3 = CONFIGS["cfg3"]
+        m.set_folds(Partitioner(np.arange(N) % c3["P"]))
+        t3 = time_fold_path(ctx, m, c3["P"], a_steps, a_warm)
+        b3 = (rank * c3["P"] // world, (rank + 1) * c3["P"] // world)
+        also["cfg3"] = {"workload": c3["name"], "value": c3["P"] / (t3["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": t3["ms_per_step"],
+                        "steps": a_steps, "warmup": a_warm, "n_gpus": world, "parallelism": f"fold-sharded x{world}", "gpu_launches": t3["launches"],
+                        "roofline": roofline_of("cfg3", c3, world, (b3[1] - b3[0]) * (N // c3["P"]), b3[1] - b3[0], t3, t3["ms_per_step"])}
+        del t3
+        c4 = CONFIGS["cfg4"]
+        X4, Y4, w4, folds4, keep4 = make_host_inputs(c4, pinned=False)
+        m4 = CVMatrix(dtype=np.float64, copy=False, device=local_rank)
+        m4.fit(X4, Y4, w4)
+        m4.set_folds(Partitioner(folds4))
+        t4 = time_fold_path(ctx, m4, c4["P"], a_steps, a_warm)
+        b4 = (rank * c4["P"] // world, (rank + 1) * c4["P"] // world)
+        also["cfg4"] = {"workload": c4["name"], "value": c4["P"] / (t4["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": t4["ms_per_step"],
+                        "steps": a_steps, "warmup": a_warm, "n_gpus": world, "parallelism": f"fold-sharded x{world}", "gpu_launches": t4["launches"],
+                        "roofline": roofline_of("cfg4", c4, world, b4[1] - b4[0], b4[1] - b4[0], t4, t4["ms_per_step"])}
+        _lib.check(m4._lib.cvmx_set_stream(m4._h, None), m4._h)
+        del t4, m4, X4, Y4, w4
+        torch.cuda.empty_cache()
+        m.set_folds(part)
+    del tm
 
     # ---- end to end through the public API, host buffers in, host arrays out ------------------------------
     e2e = None
+    e2e_res = {}
     if not args.no_e2e:
-        from cvmatrix_b200.distributed import fit_sharded_upload
-
         if world == 1:
             _lib.check(lib.cvmx_set_stream(h, None), h)
         e2e_steps = args.steps if cfg["P"] <= 1000 else max(1, min(args.steps, 2))
         out_bytes = 0
         host_out = None
+        fb0, fb1 = rank * P // world, (rank + 1) * P // world
+        chunk = min(max(fb1 - fb0, 1), 4096)
         if row_sharded and world > 1:   # pinned host buffers for the folds this rank owns
             o0, o1 = sharding.fold_block(rank, world, 0, P)
             n_own = max(o1 - o0, 1)
@@ -365,20 +535,20 @@ def main():
 
         parts = {"partitioner_ms": 0.0, "fit_ms": 0.0, "set_folds_ms": 0.0, "folds_ms": 0.0}
 
-        def e2e_step():
+        def e2e_step(Xh, Yh, wh, keep_results=False):
             nonlocal out_bytes
             t0 = time.perf_counter()
             p2 = Partitioner(folds)
             t1 = time.perf_counter()
             if world > 1:
                 # every rank uploads 1 / world of the rows over its own PCIe link; slabs are exchanged over NVLink
-                fit_sharded_upload(m, X, Y, w)
+                fit_sharded_upload(m, Xh, Yh, wh)
                 t2 = time.perf_counter()
                 m.set_folds(p2)
             else:
                 # fit + set_folds in one call: the folds partition the rows, so every row is contracted once, per fold,
                 # behind the upload (XtWX = sum of the fold Grams) and training_batch only finishes the folds
-                m.fit(X, Y, w, folds=p2)
+                m.fit(Xh, Yh, wh, folds=p2)
                 t2 = time.perf_counter()
             t3 = time.perf_counter()
             out_bytes = 0
@@ -391,21 +561,27 @@ def main():
                         out_bytes += hbuf[:n].numel() * hbuf.element_size()
                 torch.cuda.synchronize()
             else:
-                for c0 in range(f0, f1, chunk):
-                    r = m.training_batch(c0, min(f1, c0 + chunk), out=args.e2e_out)
+                for c0 in range(fb0, fb1, chunk):
+                    r = m.training_batch(c0, min(fb1, c0 + chunk), out=args.e2e_out)
                     out_bytes += r["XTX"].nbytes + r["XTY"].nbytes + 2 * r["X_mean"].nbytes + 2 * r["Y_mean"].nbytes
+                    if keep_results and c0 == fb0 and P <= 1000:
+                        for f in range(min(P, 5)):
+                            e2e_res[f] = (r["XTX"][f].copy(), r["XTY"][f].copy(),
+                                          (r["X_mean"][f].copy(), r["X_std"][f].copy(), r["Y_mean"][f].copy(), r["Y_std"][f].copy()))
             t4 = time.perf_counter()
             for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 parts[k] += v * 1e3
 
-        e2e_step()
+        if world > 1:
+            _lib.check(lib.cvmx_set_stream(h, C.c_void_p(ctx.stream.cuda_stream)), h)
+        e2e_step(X, Y, w)
         for k in parts:
             parts[k] = 0.0
-        barrier()
+        ctx.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for i in range(e2e_steps):
+            e2e_step(X, Y, w, keep_results=(i == e2e_steps - 1 and world == 1 and want_parity and not args.no_cpu_baseline))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         h2d = int(X.nbytes + Y.nbytes + w.nbytes) // world + int(part.indices.nbytes + part.offsets.nbytes)
@@ -420,40 +596,74 @@ def main():
                "includes": ("Partitioner + fit (H2D from pinned host memory" + (f": 1/{world} of the rows per rank, slabs exchanged over NVLink" if world > 1 else "; fused with the fold Grams when the folds partition the rows")
                             + ") + set_folds + all folds + D2H of every output"),
                "host_outputs": args.e2e_out, "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
+        if world == 1 and N * K * 8 <= 5e9 and P <= 1000:
+            # the same call with ordinary (pageable) numpy arrays, as a drop-in user would pass them
+            Xp, Yp, wp = np.array(X), np.array(Y), np.array(w)
+            e2e_step(Xp, Yp, wp)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                e2e_step(Xp, Yp, wp)
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - t0) / 2
+            e2e["pageable_input"] = {"value": P / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": 2,
+                                     "note": "inputs are ordinary numpy arrays: the driver stages pageable memory through its bounce buffer"}
+            del Xp, Yp, wp
 
-    # ---- CPU baseline: numpy restatement of the reference on this box's host cores (rank 0, N = 1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        from cvmatrix_oracle import OracleCVMatrix, OraclePartitioner
-
+    # ---- CPU baseline + parity: the reference on this box's host cores (rank 0) --------------------------------
+    cpu = parity = parity_e2e = None
+    if rank == 0 and ((world == 1 and not args.no_cpu_baseline) or (world > 1 and want_parity and native_res)):
+        RefCV, RefPart, kind, threads, blas = load_reference()
         t0 = time.perf_counter()
-        op = OraclePartitioner(folds)
-        orc = OracleCVMatrix(dtype=np.float64, copy=False, order="numpy")
+        op = RefPart(folds)
+        orc = RefCV(dtype=np.float64, copy=False)
         orc.fit(X, Y, w)
         t_fit = time.perf_counter() - t0
         keys = list(op.folds_dict)
-        n_f = len(keys) if P <= 5 else max(5, min(len(keys), int(12.0 / (9.0 / P if P <= 1000 else 0.005))))
-        n_f = min(n_f, 2000)
+        if world == 1:
+            n_f = len(keys) if P <= 5 else max(5, min(len(keys), int(12.0 / (9.0 / P if P <= 1000 else 0.005))))
+            n_f = min(n_f, 2000)
+            timed = keys[:n_f]
+        else:
+            timed = [keys[f] for f in sorted(native_res)]
+            n_f = len(timed)
+        ref_res = {}
+        pos_of = {k: i for i, k in enumerate(keys)}
+        needed = set(native_res) | set(e2e_res)
         t0 = time.perf_counter()
-        for k in keys[:n_f]:
-            orc.training_XTX_XTY(op.get_validation_indices(k))
+        for k in timed:
+            (rx, ry), rs = orc.training_XTX_XTY(op.get_validation_indices(k))
+            if pos_of[k] in needed:
+                ref_res[pos_of[k]] = (rx, ry, rs)
         t_folds = (time.perf_counter() - t0) * (len(keys) / n_f)
-        cpu = {"value": P / t_folds, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"full-size fit ({t_fit:.1f} s, not in value) then {n_f} of {P} folds, fold-path time scaled to {P} folds",
-               "fit_s": t_fit, "folds_s": t_folds, "e2e_value": P / (t_fit + t_folds)}
+        for pos in native_res:
+            if pos not in ref_res:     # folds outside the timed sample (leave-one-out: the sample is a prefix)
+                (rx, ry), rs = orc.training_XTX_XTY(op.get_validation_indices(keys[pos]))
+                ref_res[pos] = (rx, ry, rs)
+        if world == 1:
+            cpu = {"value": P / t_folds, "unit": UNIT, "cores": threads, "blas_threads": blas, "kind": kind,
+                   "sample": f"full-size fit ({t_fit:.1f} s, not in value) then {n_f} of {P} folds, fold-path time scaled to {P} folds",
+                   "fit_s": t_fit, "folds_s": t_folds, "e2e_value": P / (t_fit + t_folds)}
+        if want_parity:
+            what = ("timed path: plain fit + batched fold path" if world == 1 else
+                    f"timed path on {world} GPUs, fold {sorted(native_res)[0]} as returned by its owner")
+            parity = parity_summary([parity_entry(native_res[p], ref_res[p]) for p in sorted(native_res)], kind, what)
+            if e2e_res:
+                parity_e2e = parity_summary([parity_entry(e2e_res[p], ref_res[p]) for p in sorted(e2e_res) if p in ref_res], kind,
+                                            "e2e path: fit(folds=...) fused with the fold Grams, results as copied to the host")
         del orc
+    ctx.barrier()
 
     if rank == 0:
+        collective = None
+        if row_sharded and world > 1:
+            collective = ("peer-memory reduction over NVLink (symmetric memory, no all-reduce)" if (sf is not None and sf._symm is not None)
+                          else "1 NCCL all-reduce")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": ((f"rows of each fold sharded x{world} + " + ("peer-memory reduction over NVLink (symmetric memory, no all-reduce)" if (sf is not None and sf._symm is not None) else "1 NCCL all-reduce")) if row_sharded else f"fold-sharded x{world}"),
-                       "l2_policy": "inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8 else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2",
-                       "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "fit_with_h2d_s": fit_upload_s,
+            "data": "synthetic", "config": config_dict(cfg, world), "collective": collective, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "parity_e2e_path": parity_e2e, "also": also, "fit_with_h2d_s": fit_upload_s,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

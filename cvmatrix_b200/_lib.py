@@ -52,6 +52,7 @@ SIGNATURES = {
     "cvmx_ld": (_i64, [_vp]),
     "cvmx_set_scan_mode": (_i32, [_vp, _i32]),
     "cvmx_scan_launch_count": (_i64, [_vp]),
+    "cvmx_set_loo_mode": (_i32, [_vp, _i32]),
 }
 
 _lib = None

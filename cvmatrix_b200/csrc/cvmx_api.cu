@@ -84,6 +84,10 @@ struct cvmx_handle {
   bool attr_gram = false, attr_mom = false;
   // binade scan of the moment chains (kernels_scan.cuh): 0 off, 1 when the chains are the critical path, 2 always
   int scan_mode = 1;
+  // leave-one-out batches: 0 streaming form (two FMAs + reciprocal scaling per element, matrices to ~1e-15 of the
+  // reference), 1 exact form (numpy's operation order and IEEE division: bit-identical matrices for one-row folds)
+  int loo_mode = 0;
+  DevBuf loo_ops;
   // fused fit + folds (cvmx_fit_folds): raw float64 Gram of every fold of a true partition, [P][ntiles][GACC][GTHREADS],
   // valid while csr_version == fold_gram_version; cvmx_training_batch then only runs statistics + epilogue
   TableCache tc_gram, tc_finish;
@@ -119,6 +123,21 @@ int32_t fail(cvmx_t* h, int32_t code, const std::string& msg) {
       return fail(h, e__ == cudaErrorMemoryAllocation ? CVMX_ERR_NOMEM : CVMX_ERR_CUDA,                  \
                   std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
   } while (0)
+
+// Every ABI entry works on the handle's device but leaves the CALLER's current device as it found it: the current
+// device is per-thread driver state shared with torch, and cvmx_destroy runs from a Python destructor at arbitrary times.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(h) DeviceGuard guard__((h)->device); CU(h, guard__.err)
 
 enum { PROF_STATS = 0, PROF_GRAM = 1, PROF_REDUCE = 2, PROF_KINDS = 3 };
 
@@ -277,7 +296,18 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
     const dim3 grid(gx, (unsigned)((nf + SMALL_FOLDS - 1) / SMALL_FOLDS));
     bool loo = true;   // every fold of this launch has exactly one row -> specialised kernel
     for (int64_t f = f0 + c0; f < f0 + c0 + nf && loo; ++f) loo = (off[f + 1] - off[f]) == 1;
-    if (loo) {
+    if (loo && h->loo_mode == 0) {
+      // streaming form: operand rows of every fold, then 32 x 128 output tiles streamed over the folds
+      const int64_t pos0 = off[f0 + c0], ld = h->ld;
+      CU(h, h->loo_ops.reserve((size_t)nf * 4 * ld * sizeof(T)));
+      k_loo_operands<T><<<dim3((unsigned)((ld + 127) / 128), (unsigned)nf), 128, 0, h->stream>>>(
+          h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<T>());
+      const int col_tiles = (int)((h->K + h->M + LOO_TC - 1) / LOO_TC), row_tiles = (int)((h->K + LOO_TR - 1) / LOO_TR);
+      k_loo_tiles<T><<<dim3((unsigned)(col_tiles * row_tiles), (unsigned)((nf + LOO_FOLDS - 1) / LOO_FOLDS)), LOO_THREADS, 0, h->stream>>>(
+          h->Ttot.as<T>(), h->loo_ops.as<T>(), ld, h->K, h->M, col_tiles, nf, want, q.epi.out_xx, q.epi.xx_pitch, q.epi.xx_stride,
+          q.epi.out_xy, q.epi.xy_pitch, q.epi.xy_stride);
+      h->launches++;
+    } else if (loo) {
       const int64_t pos0 = off[f0 + c0];
       switch (h->flags & 15u) {
 #define CVMX_LOO_CASE(F) case F: k_loo_folds<T, F><<<grid, STHREADS, 0, h->stream>>>(q, pos0); break;
@@ -1307,7 +1337,9 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   h->device = device; h->dtype = dtype; h->flags = flags & 15u; h->ddof = ddof; h->resolution = resolution;
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
-  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+  if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
+  DeviceGuard guard__(device);
+  if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
     return fail(nullptr, CVMX_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -1332,9 +1364,9 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
 
 int32_t cvmx_destroy(cvmx_t* h) {
   if (!h) return CVMX_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard__(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+  for (DevBuf* b : {&h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
@@ -1357,6 +1389,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
 
 int32_t cvmx_set_stream(cvmx_t* h, void* s) {
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
+  ON_DEVICE(h);
   cudaStreamSynchronize(h->stream);
   h->stream = s ? (cudaStream_t)s : h->own_stream;
   return CVMX_OK;
@@ -1364,7 +1397,7 @@ int32_t cvmx_set_stream(cvmx_t* h, void* s) {
 
 int32_t cvmx_sync(cvmx_t* h) {
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(h, cudaStreamSynchronize(h->stream));
   return CVMX_OK;
 }
@@ -1374,7 +1407,7 @@ int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
   if (!X || N < 0 || K <= 0 || ldx < K || M < 0 || (M > 0 && (!Y || ldy < M)) || g0 < 0 || g1 > N || g0 > g1)
     return fail(h, CVMX_ERR_INVALID, "cvmx_fit: bad shape arguments");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   if (!Y) M = 0;
   return h->dtype == CVMX_F64 ? fit_impl<double>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1)
                               : fit_impl<float>(h, X, N, K, ldx, Y, M, ldy, w, mem, g0, g1);
@@ -1384,7 +1417,7 @@ int32_t cvmx_fit(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
 int32_t cvmx_fit_begin(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weighted, int64_t max_block_rows) {
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
   if (N < 0 || K <= 0 || M < 0 || max_block_rows <= 0) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_begin: bad shape arguments");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64 ? fit_begin_impl<double>(h, N, K, M, weighted, max_block_rows)
                               : fit_begin_impl<float>(h, N, K, M, weighted, max_block_rows);
 }
@@ -1396,7 +1429,7 @@ int32_t cvmx_fit_rows(cvmx_t* h, int64_t row0, int64_t nrows, const void* X, int
       (h->weighted && nrows > 0 && !w))
     return fail(h, CVMX_ERR_INVALID, "cvmx_fit_rows: bad block arguments");
   if (nrows == 0) return CVMX_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64 ? fit_rows_impl<double>(h, row0, nrows, X, ldx, Y, ldy, w, mem, gram)
                               : fit_rows_impl<float>(h, row0, nrows, X, ldx, Y, ldy, w, mem, gram);
 }
@@ -1404,7 +1437,7 @@ int32_t cvmx_fit_rows(cvmx_t* h, int64_t row0, int64_t nrows, const void* X, int
 int32_t cvmx_fit_end(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
   if (!h || !h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end: call cvmx_fit_begin first");
   if (n_col_shards < 1 || col_shard < 0 || col_shard >= n_col_shards) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end: bad column shard");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64 ? fit_end_impl<double>(h, col_shard, n_col_shards) : fit_end_impl<float>(h, col_shard, n_col_shards);
 }
 
@@ -1440,7 +1473,7 @@ int32_t cvmx_commit_totals(cvmx_t* h) {
 int32_t cvmx_get_totals(cvmx_t* h, void* XTX, void* XTY, void* sum_X, void* sum_Y, void* sum_sq_X, void* sum_sq_Y,
                         double* sum_w, int64_t* nnz_w) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_get_totals: fit first");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const size_t sz = esz(h);
   const int64_t K = h->K, M = h->M, ld = h->ld;
   const char* T = h->Ttot.as<char>();
@@ -1461,7 +1494,7 @@ int32_t cvmx_get_totals(cvmx_t* h, void* XTX, void* XTY, void* sum_X, void* sum_
 int32_t cvmx_set_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P, int32_t mem) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_set_folds: fit first");
   if (!offsets || P < 0) return fail(h, CVMX_ERR_INVALID, "cvmx_set_folds: bad arguments");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   h->h_off.resize(P + 1);
   if (mem == CVMX_HOST) std::memcpy(h->h_off.data(), offsets, (P + 1) * sizeof(int64_t));
   else CU(h, cudaMemcpy(h->h_off.data(), offsets, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -1483,7 +1516,7 @@ int32_t cvmx_fit_folds(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t l
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
   if (!X || N < 0 || K <= 0 || ldx < K || M < 0 || (M > 0 && (!Y || ldy < M)) || !offsets || P < 0 || (P > 0 && offsets[P] > 0 && !indices))
     return fail(h, CVMX_ERR_INVALID, "cvmx_fit_folds: bad arguments");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   if (!Y) M = 0;
   if (offsets[0] != 0) return fail(h, CVMX_ERR_INVALID, "offsets[0] must be 0");
   for (int64_t f = 0; f < P; ++f)
@@ -1513,7 +1546,7 @@ int32_t cvmx_training_batch(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, vo
                             int32_t* ostatus, int32_t mem) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_training_batch: fit first");
   if (f0 < 0 || f1 > h->P || f0 > f1) return fail(h, CVMX_ERR_INVALID, "cvmx_training_batch: fold range outside the CSR");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64
              ? training_impl<double>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), h->h_off.data(), f0, f1, want, oxx, oxy,
                                      ostats, oscal, ostatus, mem, true)
@@ -1525,7 +1558,7 @@ int32_t cvmx_training_indices(cvmx_t* h, const int64_t* val, int64_t n_val, int3
                               void* ostats, void* oscal, int32_t* ostatus, int32_t out_mem) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_training_indices: fit first");
   if (n_val < 0 || (n_val > 0 && !val)) return fail(h, CVMX_ERR_INVALID, "cvmx_training_indices: bad arguments");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const int64_t off[2] = {0, n_val};
   int32_t rc = upload_csr(h, h->a_off, h->a_idx, off, val, 1, n_val, idx_mem);
   if (rc) return rc;
@@ -1541,7 +1574,7 @@ int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard,
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats: fit first");
   if (f0 < 0 || f1 > h->P || f0 >= f1 || n_col_shards < 1 || col_shard < 0 || col_shard >= n_col_shards)
     return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats: bad fold range or shard");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   int32_t rc = h->dtype == CVMX_F64 ? sharded_stats<double>(h, f0, f1, col_shard, n_col_shards)
                                     : sharded_stats<float>(h, f0, f1, col_shard, n_col_shards);
   if (stats_dev) *stats_dev = h->stats.p;
@@ -1551,7 +1584,7 @@ int32_t cvmx_sharded_stats(cvmx_t* h, int64_t f0, int64_t f1, int32_t col_shard,
 
 int32_t cvmx_sharded_stats_wait(cvmx_t* h) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_stats_wait: fit first");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   return CVMX_OK;
 }
@@ -1568,7 +1601,7 @@ int32_t cvmx_sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int3
   if (f0 < 0 || f1 > h->P || f0 >= f1 || n_row_shards < 1 || row_shard < 0 || row_shard >= n_row_shards || !gram_dev)
     return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_gram: bad fold range, shard or buffer");
   if ((want & CVMX_WANT_XTY) && h->M == 0) return fail(h, CVMX_ERR_NO_Y, "Response variables `Y` are not provided.");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64 ? sharded_gram<double>(h, f0, f1, want, row_shard, n_row_shards, gram_dev)
                               : sharded_gram<float>(h, f0, f1, want, row_shard, n_row_shards, gram_dev);
 }
@@ -1578,7 +1611,7 @@ int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1,
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish: fit first");
   if (batch_f0 < 0 || f0 < batch_f0 || f1 > h->P || f0 > f1 || !gram_dev)
     return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish: bad fold range or buffer");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   int32_t rc = h->dtype == CVMX_F64 ? sharded_finish<double>(h, batch_f0, f0, f1, want, gram_dev, (double*)oxx, (double*)oxy)
                                     : sharded_finish<float>(h, batch_f0, f0, f1, want, gram_dev, (float*)oxx, (float*)oxy);
   if (rc || f1 == f0) return rc;
@@ -1607,7 +1640,7 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
   if (batch_f0 < 0 || f0 < batch_f0 || f1 > batch_f1 || batch_f1 > h->P || f0 > f1 || !peer_bufs || n_peers < 1 || n_peers > 8)
     return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: bad fold range or peer list (at most 8 peers)");
   if (h->dtype != CVMX_F64) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: float64 handles only");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   // statistics rows of the whole batch: sum of the peers' column shards, straight into the statistics buffer
   const int64_t nst = (batch_f1 - batch_f0) * 2 * h->ld;
   PeerList pl8;
@@ -1636,14 +1669,14 @@ int32_t cvmx_validation_rows(cvmx_t* h, int64_t fold, const void* stats, uint32_
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: fit first");
   if (fold < 0 || fold >= h->P) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: fold outside the CSR");
   if (apply && !stats) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: statistics needed for centring / scaling");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   return h->dtype == CVMX_F64 ? validation_rows_impl<double>(h, fold, stats, apply, out_X, out_Y, mem)
                               : validation_rows_impl<float>(h, fold, stats, apply, out_X, out_Y, mem);
 }
 
 int32_t cvmx_profile_enable(cvmx_t* h, int32_t on) {
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(h, cudaStreamSynchronize(h->stream));
   h->prof = on != 0;
   h->prof_spans.clear();
@@ -1653,7 +1686,7 @@ int32_t cvmx_profile_enable(cvmx_t* h, int32_t on) {
 
 int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count) {
   if (!h) return fail(nullptr, CVMX_ERR_INVALID, "handle is NULL");
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   CU(h, cudaStreamSynchronize(h->stream));
   for (int k = 0; k < PROF_KINDS; ++k) { if (ms) ms[k] = 0; if (count) count[k] = 0; }
   for (auto& sp : h->prof_spans) {
@@ -1694,6 +1727,11 @@ int64_t cvmx_scan_launch_count(const cvmx_t* h) { return h ? h->scan_launches : 
 int32_t cvmx_set_scan_mode(cvmx_t* h, int32_t mode) {
   if (!h || mode < 0 || mode > 2) return fail(h, CVMX_ERR_INVALID, "cvmx_set_scan_mode: mode must be 0, 1 or 2");
   h->scan_mode = mode;
+  return CVMX_OK;
+}
+int32_t cvmx_set_loo_mode(cvmx_t* h, int32_t mode) {
+  if (!h || mode < 0 || mode > 1) return fail(h, CVMX_ERR_INVALID, "cvmx_set_loo_mode: mode must be 0 (streaming) or 1 (exact)");
+  h->loo_mode = mode;
   return CVMX_OK;
 }
 int64_t cvmx_ld(const cvmx_t* h) { return h ? h->ld : 0; }

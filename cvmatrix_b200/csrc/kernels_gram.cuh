@@ -776,4 +776,122 @@ __global__ void __launch_bounds__(STHREADS, 3) k_loo_folds(const SmallParams<T> 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Leave-one-out, streaming form (default).  The result of fold f is
+//   A_ij = (T_ij - w x_i z_j - sw m_i m_j) / (s_i s_j)                       (cvmatrix/cvmatrix.py:1001-1009)
+// and the fold is bound by WRITING its K x (K + M) result.  Matrices owe the reference 1e-12, not its bits, so the
+// per-element work is cut to two FMAs and two multiplications on operand rows prepared once per fold:
+//   v_c = rn(sqrt(w) z_c)         u_c = rn(sqrt(sw) m_c)  (0 where the flags do not centre)         r_c = 1 / s_c  (1 where
+//   they do not scale)            A_ij = fma(-v_i, v_j, fma(-urow_i, ucol_j, T_ij)) * (r_i * r_j)
+// Every product is symmetric in (i, j) bit for bit (an FMA rounds the exact product once), so XTX comes out exactly
+// symmetric without mirroring.  `urow` differs from `ucol` only for X columns when center_Y is set without center_X:
+// XTY is then centred (row side needs the X means) but XTX is not.
+// k_loo_operands: one thread per (fold, column).  k_loo_tiles: CTA = 32 x 128 output tile (warp = 4 rows, lane = 4
+// columns, the 16 totals in registers) streamed over LOO_FOLDS folds; per fold a thread loads 6 + 6 16-byte operand
+// vectors (the row side is warp-uniform) and stores 4 x 32 bytes, a warp 4 x 1 KB of contiguous output rows.
+// The exact form k_loo_folds (IEEE division, numpy's operation order, bit-identical to the reference for one-row folds)
+// stays selectable (cvmx_set_loo_mode).
+// ------------------------------------------------------------------------------------------------------
+constexpr int LOO_TR = 32, LOO_TC = 128, LOO_FOLDS = 32, LOO_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_loo_operands(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t K, int64_t M,
+                                                      const int64_t* __restrict__ rows, const T* __restrict__ stats,
+                                                      const FoldScalars* __restrict__ fs, uint32_t flags, T* __restrict__ opnd) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t f = blockIdx.y;
+  if (c >= ld) return;
+  T* o = opnd + (size_t)f * 4 * ld;
+  if (c >= K + M) { o[c] = T(0); o[ld + c] = T(0); o[2 * ld + c] = T(1); o[3 * ld + c] = T(0); return; }
+  const bool cX = flags & 1, cY = flags & 2, sX = flags & 4, sY = flags & 8;
+  const bool isX = c < K;
+  const int64_t row = rows[f];
+  const T mean = stats[(size_t)f * 2 * ld + c], sd = stats[(size_t)f * 2 * ld + ld + c];
+  const T rsw = Rn<T>::sqrt((T)fs[f].sw);
+  o[c] = Rn<T>::mul(Rn<T>::sqrt(w[row]), Z[row * ld + c]);
+  const T um = Rn<T>::mul(rsw, mean);
+  o[ld + c] = (isX ? cX : (cX || cY)) ? um : T(0);          // column side
+  o[2 * ld + c] = (isX ? sX : sY) ? Rn<T>::div(T(1), sd) : T(1);
+  o[3 * ld + c] = (isX && (cX || cY)) ? um : T(0);          // row side (X columns only)
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<double> { double v[4]; __device__ __forceinline__ void load(const double* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; } };
+template <> struct Vec4<float> { float v[4]; __device__ __forceinline__ void load(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; } };
+
+template <typename T>
+__global__ void __launch_bounds__(LOO_THREADS, 2) k_loo_tiles(const T* __restrict__ Ttot, const T* __restrict__ opnd, int64_t ld, int64_t K,
+                                                              int64_t M, int col_tiles, int64_t nfolds, uint32_t want,
+                                                              T* __restrict__ out_xx, int64_t xx_pitch, int64_t xx_stride,
+                                                              T* __restrict__ out_xy, int64_t xy_pitch, int64_t xy_stride) {
+  typedef typename GramCfg<T>::vec2 vec2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles;
+  const int64_t i0 = (int64_t)rt * LOO_TR + 4 * warp, j0 = (int64_t)ct * LOO_TC + 4 * lane;
+  const int64_t C = K + M;
+  const int64_t fbeg = (int64_t)blockIdx.y * LOO_FOLDS;
+  const int nf = (int)(min(nfolds, fbeg + LOO_FOLDS) - fbeg);
+  const bool wxx = want & 1, wxy = want & 2;
+  if (i0 >= K || j0 >= C) return;
+  if (!((wxx && j0 < K) || (wxy && j0 + 3 >= K))) return;
+  const int nr = (int)min((int64_t)4, K - i0);                       // live rows of this thread
+  // 16-byte stores need an even element offset on every row (j0 is a multiple of 4)
+  const bool fast = wxx && j0 + 3 < K && (xx_pitch % 2 == 0) && (xx_stride % 2 == 0) &&
+                    (reinterpret_cast<uintptr_t>(out_xx) % (2 * sizeof(T)) == 0);
+
+  T tt[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    Vec4<T> t;
+    t.load(Ttot + min(i0 + a, K - 1) * ld + j0);                     // j0 + 3 < ld (ld % 32 == 0)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) tt[a][b] = t.v[b];
+  }
+  const T* __restrict__ op = opnd + (size_t)fbeg * 4 * ld;
+  T* oxx = out_xx + (size_t)fbeg * xx_stride + i0 * xx_pitch + j0;
+  T* oxy = out_xy + (size_t)fbeg * xy_stride + i0 * xy_pitch;
+
+#pragma unroll 1
+  for (int f = 0; f < nf; ++f) {
+    Vec4<T> vj, uj, rj, vi, ui, ri;
+    vj.load(op + j0); uj.load(op + ld + j0); rj.load(op + 2 * ld + j0);
+    vi.load(op + i0); ri.load(op + 2 * ld + i0); ui.load(op + 3 * ld + i0);   // warp-uniform (i0 + 3 < ld)
+    T o[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        o[a][b] = Rn<T>::mul(fma(-vi.v[a], vj.v[b], fma(-ui.v[a], uj.v[b], tt[a][b])), Rn<T>::mul(ri.v[a], rj.v[b]));
+    if (fast) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a < nr) {
+          vec2 lo, hi;
+          lo.x = o[a][0]; lo.y = o[a][1]; hi.x = o[a][2]; hi.y = o[a][3];
+          *reinterpret_cast<vec2*>(oxx + a * xx_pitch) = lo;
+          *reinterpret_cast<vec2*>(oxx + a * xx_pitch + 2) = hi;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a >= nr) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int64_t jj = j0 + b;
+          if (jj < K) { if (wxx) oxx[a * xx_pitch + b] = o[a][b]; }
+          else if (jj < C && wxy) oxy[a * xy_pitch + (jj - K)] = o[a][b];
+        }
+      }
+    }
+    op += 4 * ld;
+    oxx += xx_stride;
+    oxy += xy_stride;
+  }
+}
+
 }  // namespace cvmx

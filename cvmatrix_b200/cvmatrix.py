@@ -120,7 +120,12 @@ class CVMatrix:
     # ---- pickling (the reference object is a plain picklable container that callers ship to worker processes,
     # cvmatrix/partitioner.py:26-31): device state is dropped and rebuilt from the host arrays on load -----------
     def __getstate__(self):
+        if getattr(self, "_streamed", False) and self.X is None:
+            raise TypeError("a CVMatrix fitted through fit_begin / fit_rows / fit_end keeps its rows on the device only and "
+                            "cannot be pickled; fit from host arrays instead")
         state = {k: v for k, v in self.__dict__.items() if k not in ("_lib", "_h", "_partitioner", "_pinned_pool")}
+        if getattr(self, "_n_folds", 0) and getattr(self, "_fold_indices", None) is None:
+            state["_n_folds"] = 0       # the CSR lives on the device only (should not happen: set_folds keeps a host copy)
         return state
 
     def __setstate__(self, state):
@@ -133,12 +138,16 @@ class CVMatrix:
             float(self.resolution), C.byref(self._h),
         )
         _lib.check(rc, None)
+        self._streamed = False
+        n_folds, offsets, indices = state.get("_n_folds", 0), state.get("_offsets"), state.get("_fold_indices")
         if self.X is not None:
             keep, self.copy = self.copy, False   # the unpickled arrays are already private copies
             try:
-                self.fit(self.X, self.Y, None if self.weights is None else self.weights)
+                self.fit(self.X, self.Y, None if self.weights is None else self.weights)   # resets the fold state
             finally:
                 self.copy = keep
+            if n_folds and offsets is not None and indices is not None:
+                self._upload_csr(offsets, indices)   # the validation sets travel with the object
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -192,6 +201,7 @@ class CVMatrix:
             raise ValueError("weights must have one entry per row of X")
         self._partitioner = None
         self._n_folds = 0
+        self._offsets = self._fold_indices = None
 
         Xd, ldx = self._rows(self.X)
         Yd, ldy = self._rows(self.Y) if self.Y is not None else (None, 0)
@@ -209,6 +219,7 @@ class CVMatrix:
             self._partitioner = folds
             self._n_folds = offsets.size - 1
             self._offsets = offsets
+            self._fold_indices = indices
         else:
             rc = self._lib.cvmx_fit(self._h, _ptr(Xd), self.N, self.K, ldx, _ptr(Yd), self.M or 0, ldy, _ptr(wd), _lib.HOST, g0, g1)
             _lib.check(rc, self._h)
@@ -221,6 +232,8 @@ class CVMatrix:
         self.X = self.Y = self.weights = None
         self.N, self.K, self.M = int(N), int(K), (int(M) if M else None)
         self._partitioner = None
+        self._n_folds = 0
+        self._offsets = self._fold_indices = None
         self._streamed = False
         self._stream_weighted = bool(weighted)
         _lib.check(self._lib.cvmx_fit_begin(self._h, int(N), int(K), int(M or 0), int(bool(weighted)), int(max_block_rows)), self._h)
@@ -250,7 +263,12 @@ class CVMatrix:
         ``gram`` the block's weighted Gram is added to the totals (every row by exactly one rank)."""
         xp, ldx, mem, kx = self._block(X, self.dtype)
         yp, ldy, memy, ky = self._block(Y, self.dtype)
-        wp, _, memw, kw = self._block(weights, self.dtype)
+        if weights is not None:   # the library reads nrows CONTIGUOUS weights: flatten strided views first
+            weights = (weights.reshape(-1).contiguous() if hasattr(weights, "data_ptr")
+                       else np.ascontiguousarray(np.asarray(weights, dtype=self.dtype).reshape(-1)))
+        wp, ldw, memw, kw = self._block(weights, self.dtype)
+        if wp is not None and (ldw != 1 or int(kw.shape[0]) != int(kx.shape[0])):
+            raise ValueError("weights must hold one contiguous value per row of the block")
         if (yp is not None and memy != mem) or (wp is not None and memw != mem):
             raise ValueError("X, Y and weights of a block must live in the same memory (all host or all device)")
         nrows = int(kx.shape[0])
@@ -413,12 +431,16 @@ class CVMatrix:
             if sets:
                 np.cumsum([s.size for s in sets], out=offsets[1:])
             indices = np.concatenate(sets) if sets else np.zeros(0, np.int64)
+        self._upload_csr(offsets, indices)
+
+    def _upload_csr(self, offsets, indices) -> None:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int64)
         rc = self._lib.cvmx_set_folds(self._h, _ptr(offsets), _ptr(indices), offsets.size - 1, _lib.HOST)
         _lib.check(rc, self._h)
         self._n_folds = offsets.size - 1
         self._offsets = offsets
+        self._fold_indices = indices    # host copy: pickling re-uploads it (cvmatrix/partitioner.py:26-31 ships folds separately)
 
     def training_batch(self, fold_begin: int = 0, fold_end: Optional[int] = None, return_XTX: bool = True,
                        return_XTY: bool = True, out: str = "numpy", check: bool = True):
@@ -445,6 +467,7 @@ class CVMatrix:
         want = (_lib.WANT_XTX if return_XTX else 0) | (_lib.WANT_XTY if return_XTY else 0)
         cX, cY, sX, sY = self.center_X, self.center_Y, self.scale_X, self.scale_Y
         need = (cX or (return_XTY and cY), sX, return_XTY and (cX or cY), return_XTY and sY)
+        bound, prev_stream = False, None
         if out == "torch":
             import torch
 
@@ -462,6 +485,7 @@ class CVMatrix:
             ts = torch.cuda.current_stream(dev)
             if ts.cuda_stream:
                 _lib.check(self._lib.cvmx_set_stream(self._h, C.c_void_p(ts.cuda_stream)), self._h)
+                bound = True
             else:
                 ts.synchronize()
         elif out == "pinned":
@@ -485,10 +509,12 @@ class CVMatrix:
             mem = _lib.HOST
         else:
             raise ValueError("out must be 'numpy', 'pinned' or 'torch'")
-        rc = self._lib.cvmx_training_batch(self._h, fold_begin, fold_end, want, p(XTX), p(XTY), p(stats), p(scal), p(status), mem)
-        _lib.check(rc, self._h)
-        if out == "torch":
-            _lib.check(self._lib.cvmx_set_stream(self._h, None), self._h)  # syncs, back to the private stream
+        try:
+            rc = self._lib.cvmx_training_batch(self._h, fold_begin, fold_end, want, p(XTX), p(XTY), p(stats), p(scal), p(status), mem)
+            _lib.check(rc, self._h)
+        finally:
+            if out == "torch" and bound:   # always unbind: a failed call must not leave the handle on the caller's stream
+                self._lib.cvmx_set_stream(self._h, prev_stream)  # syncs, back to the stream the handle was on
         if check:
             st = status.cpu().numpy() if out == "torch" else status
             for s in np.unique(st):
@@ -563,6 +589,11 @@ class CVMatrix:
         0 dependent-add chains only, 1 (default) the bit-identical binade scan when the chains are on the critical
         path, 2 the scan whenever a fold has >= 1024 rows."""
         _lib.check(self._lib.cvmx_set_scan_mode(self._h, int(mode)), self._h)
+
+    def set_loo_mode(self, mode: int) -> None:
+        """Leave-one-out batches (include/cvmx.h, cvmx_set_loo_mode): 0 (default) streaming form, matrices within
+        ~1e-15 of the reference; 1 exact form, matrices bit-identical to the reference for one-row folds."""
+        _lib.check(self._lib.cvmx_set_loo_mode(self._h, int(mode)), self._h)
 
     @property
     def folds_cached(self) -> bool:

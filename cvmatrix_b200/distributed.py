@@ -56,11 +56,16 @@ class ShardedFolds:
         self._symm = None        # (buffer, handle, elements per half, peer pointer arrays per half)
         self._step = 0
 
+    @property
+    def want(self) -> int:
+        """XTX always; XTY only when the model was fitted with Y (the reference supports X-only use: training_XTX)."""
+        return _lib.WANT_XTX | (_lib.WANT_XTY if (self.cvm.M or 0) else 0)
+
     def alloc_outputs(self, n_folds: int):
         t, K, M = self.torch, self.cvm.K, self.cvm.M or 0
         return dict(
             XTX=t.empty((n_folds, K, K), dtype=self.tdt, device=self.dev),
-            XTY=t.empty((n_folds, K, M), dtype=self.tdt, device=self.dev),
+            XTY=t.empty((n_folds, K, M), dtype=self.tdt, device=self.dev) if M else None,
             stats=t.empty((n_folds, 2, K + M), dtype=self.tdt, device=self.dev),
             scal=t.empty((n_folds, 2), dtype=self.tdt, device=self.dev),
             status=t.empty((n_folds,), dtype=t.int32, device=self.dev),
@@ -101,17 +106,18 @@ class ShardedFolds:
         o0, o1 = sharding.fold_block(self.rank, self.world, f0, f1)
         if out is None:
             out = self.alloc_outputs(max(o1 - o0, 1))
-        vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
+        want = self.want
         if not row_sharded:
             if o1 > o0:
-                _lib.check(lib.cvmx_training_batch(h, o0, o1, 3, vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]), vp(out["scal"]),
+                _lib.check(lib.cvmx_training_batch(h, o0, o1, want, vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]), vp(out["scal"]),
                                                    vp(out["status"]), _lib.DEVICE), h)
             return dict(out, fold_begin=o0, fold_end=o1)
         # ---- few large folds: rows of every fold split across ranks --------------------------------------
         sp, sc = C.c_void_p(), C.c_int64()
         shards = self.emulate_shards or self.world
         _lib.check(lib.cvmx_sharded_stats(h, f0, f1, self.rank, shards, C.byref(sp), C.byref(sc)), h)
-        n = lib.cvmx_sharded_gram_count(h, f0, f1, 3)
+        n = lib.cvmx_sharded_gram_count(h, f0, f1, want)
         half_elems = n + sc.value
         if self.use_peers and self.world > 1 and (self._symm is None or self._symm[2] < half_elems):
             self._symm = self._setup_symm(half_elems)
@@ -120,19 +126,19 @@ class ShardedFolds:
             half = self._step & 1            # two halves alternate: a peer may still read step i while step i + 1 is written
             self._step += 1
             gram = buf[half * cap: half * cap + n]
-            _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, shards, vp(gram)), h)
+            _lib.check(lib.cvmx_sharded_gram(h, f0, f1, want, self.rank, shards, vp(gram)), h)
             _lib.check(lib.cvmx_sharded_stats_wait(h), h)
             stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8"), device=self.dev)
             buf[half * cap + n: half * cap + n + sc.value].copy_(stats)
             hdl.barrier(channel=0)           # every rank's Grams and statistics rows are complete and visible
-            _lib.check(lib.cvmx_sharded_finish_peers(h, f0, f1, o0, o1, 3, ptrs[half], self.world, n, vp(out["XTX"]), vp(out["XTY"]),
+            _lib.check(lib.cvmx_sharded_finish_peers(h, f0, f1, o0, o1, want, ptrs[half], self.world, n, vp(out["XTX"]), vp(out["XTY"]),
                                                      vp(out["stats"]), vp(out["scal"]), vp(out["status"])), h)
             return dict(out, fold_begin=o0, fold_end=o1)
         # one buffer for both reductions: [raw Grams | statistics rows widened to float64] -> ONE all-reduce
         if self._gram is None or self._gram.numel() < n + sc.value:
             self._gram = t.empty((n + sc.value,), dtype=t.float64, device=self.dev)
         gram = self._gram[:n]
-        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, 3, self.rank, shards, vp(gram)), h)
+        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, want, self.rank, shards, vp(gram)), h)
         _lib.check(lib.cvmx_sharded_stats_wait(h), h)   # the chains ran on a side stream beside the Gram kernel
         if self.world > 1:
             stats = t.as_tensor(_DevArray(sp.value, sc.value, "<f8" if self.tdt == t.float64 else "<f4"), device=self.dev)
@@ -140,7 +146,7 @@ class ShardedFolds:
             tail.copy_(stats)
             self.dist.all_reduce(self._gram[:n + sc.value], group=self.group)
             stats.copy_(tail)   # foreign entries were zero: the sum is exact in either dtype
-        _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, 3, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
+        _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, want, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
                                            vp(out["scal"]), vp(out["status"])), h)
         return dict(out, fold_begin=o0, fold_end=o1)
 

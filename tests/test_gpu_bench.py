@@ -27,4 +27,7 @@ def test_native_arm_json_line():
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     roof = d["roofline"]
     assert roof["bound"] in ("hbm", "tensor") and roof["peak"] > 0 and roof["achieved"] > 0 and roof["kernel"].startswith("k_gram")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    par = d["parity"]
+    assert par["stats_bit_exact"] is True and par["xtx"] <= 1e-12 and par["xty"] <= 1e-12 and par["joint"] <= 1e-12 and par["folds_checked"] == 4
+    assert d["parity_e2e_path"]["stats_bit_exact"] is True and d["parity_e2e_path"]["joint"] <= 1e-12

@@ -110,12 +110,74 @@ def test_cfg4_leave_one_out_full_size():
     # a 2000-fold device-resident chunk: exact symmetry and finite values everywhere
     dev = m.training_batch(4000, 6000, out="torch")
     assert torch.equal(dev["XTX"], dev["XTX"].transpose(1, 2)) and bool(torch.isfinite(dev["XTX"]).all())
-    # un-preprocessed LOO downdate is T - rn(w x_i) x_j exactly, given our own totals
+    # exact form (cvmx_set_loo_mode 1): same folds to the same tolerance, and the un-preprocessed LOO downdate is
+    # T - rn(w x_i) x_j bit for bit, given our own totals
+    m.set_loo_mode(1)
+    for f in (0, 9_999, 19_999):
+        out = m.training_batch(f, f + 1)
+        _check_fold(out, 0, orc.fold(np.array([f])), xty_tol=1e-12)
     m0 = CVMatrix(False, False, False, False, copy=False)
     m0.fit(X, Y, w)
     m0.set_folds(part)
+    fast = m0.training_batch(123, 131)
+    m0.set_loo_mode(1)
     out = m0.training_batch(123, 131)
     for pos, f in enumerate(range(123, 131)):
         wx = X[f] * w[f]
         assert np.array_equal(np.triu(out["XTX"][pos]), np.triu(m0.XTX - np.outer(wx, X[f])))
         assert np.array_equal(out["XTY"][pos], m0.XTY - np.outer(wx, Y[f]))
+        # streaming form: within a few ulps of the totals' magnitude of the exact one
+        assert rel_fro(fast["XTX"][pos], out["XTX"][pos]) <= 1e-15 and rel_fro(fast["XTY"][pos], out["XTY"][pos]) <= 1e-15
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cfg5_reduced_wide_k(dtype):
+    """BASELINE.json config 5 (K = 5000, M = 100, 10 folds, weighted, center + scale) at N = 40 000 rows - the reduced
+    size SURVEY.md 8(d) prescribes for parity (the full N = 2M matrix is 80 GB) - against the numpy oracle: 40 x 41 / 2
+    upper-triangular tiles + mirror, the wide-K unit plan, statistics over 5100 columns.  float64: XTX, XTY and the
+    joint matrix to 1e-12, statistics bit-exact.  float32: raw (un-centred) products to 1e-5; centred matrices inside
+    the reference's own float32 error band around the float64 evaluation (numpy-float32 is not accurate to 1e-5 there)."""
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    N, K, M, P = 40_000, 5000, 100, 10
+    X, Y, w, folds = make_inputs(N, K, M, P, dtype=dtype, seed=5)
+    part = Partitioner(folds)
+    orc = OracleCVMatrix(dtype=dtype, copy=False)
+    orc.fit(X, Y, w)
+    m = CVMatrix(dtype=dtype, copy=False)
+    m.fit(X, Y, w)
+    f64 = dtype == np.float64
+    assert rel_fro(m.XTX, orc.XTX) <= (1e-14 if f64 else 1e-6) and rel_fro(m.XTY, orc.XTY) <= (1e-14 if f64 else 1e-6)
+    assert np.array_equal(m.XTX, m.XTX.T)
+    assert np.array_equal(m.sum_X, orc.sum_X) and np.array_equal(m.sum_sq_X, orc.sum_sq_X)
+    assert np.array_equal(m.sum_Y, orc.sum_Y) and np.array_equal(m.sum_sq_Y, orc.sum_sq_Y)
+    assert m.sum_w == orc.sum_w and m.num_nonzero_w == orc.nnz_w
+    m.set_folds(part)
+    o64 = None
+    if not f64:
+        o64 = OracleCVMatrix(dtype=np.float64, copy=False)
+        o64.fit(X.astype(np.float64), Y.astype(np.float64), w.astype(np.float64))
+    for f in (0, 7):
+        out = m.training_batch(f, f + 1)
+        val = part.get_validation_indices(f)
+        r = orc.fold(val)
+        for name, g in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
+            assert np.array_equal(out[name][0], g), (f, name)
+        XTX, XTY = out["XTX"][0], out["XTY"][0]
+        assert np.array_equal(XTX, XTX.T)
+        if f64:
+            _check_fold(out, 0, r, xty_tol=1e-12)
+        else:
+            t = o64.fold(val)
+            for got, ref32, truth in ((XTX, r.XTX, t.XTX), (XTY, r.XTY, t.XTY)):
+                e_ref, e_us = rel_fro(ref32, truth), rel_fro(got, truth)
+                assert e_us <= 1.5 * e_ref + 1e-5 and rel_fro(got, ref32) <= 2.5 * e_ref + 1e-5, (f, e_us, e_ref, rel_fro(got, ref32))
+    if not f64:   # raw products: the regime where 1e-5 against numpy-float32 is meaningful
+        m0 = CVMatrix(False, False, False, False, dtype=dtype, copy=False)
+        m0.fit(X, Y, w)
+        o0 = OracleCVMatrix(False, False, False, False, dtype=dtype, copy=False)
+        o0.fit(X, Y, w)
+        val = part.get_validation_indices(3)
+        (XTX, XTY), _ = m0.training_XTX_XTY(val)
+        r = o0.fold(val)
+        assert rel_fro(XTX, r.XTX) <= 1e-5 and rel_fro(XTY, r.XTY) <= 1e-5

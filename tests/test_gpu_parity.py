@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 STATS = ("X_mean", "X_std", "Y_mean", "Y_std")
 TOL = {"float64": 1e-12, "float32": 1e-5}
+MAX_ABSOLUTE_ESCAPES = 40   # of ~2000 golden matrix checks (measured on B200: see profiles/r02_parity.json)
 
 
 def _unpack(method, res):
@@ -29,20 +30,34 @@ def _unpack(method, res):
     return {method.split("_")[1]: res[0]}, res[1]
 
 
+ESCAPES = {"nonfinite": 0, "absolute": 0, "checked": 0}
+
+
 def _mat_ok(a, g, total, tol, scaled):
-    """relFro <= tol, or - for folds whose centred matrix is pure cancellation residue - an absolute
-    error below tol * ||total|| (only meaningful when no scaling is applied)."""
+    """relFro <= tol.  Two escapes, both COUNTED (test_golden_fixtures asserts the counts):
+    * a non-finite expectation (degenerate unweighted folds) must be non-finite in the same places and equal elsewhere;
+    * an UNSCALED centred matrix that is pure cancellation residue (a validation set holding nearly every row) is
+      held to an absolute error of tol * ||total|| instead - the rounding floor of T - G for any evaluation order."""
+    ESCAPES["checked"] += 1
     if not np.all(np.isfinite(g)):
-        return True
+        ESCAPES["nonfinite"] += 1
+        fin = np.isfinite(g)
+        return np.array_equal(np.isnan(a), np.isnan(g)) and np.array_equal(np.isposinf(a), np.isposinf(g)) and \
+            np.array_equal(np.isneginf(a), np.isneginf(g)) and (not fin.any() or np.allclose(a[fin], g[fin], rtol=tol, atol=0))
     if rel_fro(a, g) <= tol:
         return True
-    return (not scaled) and np.linalg.norm(a.astype(np.float64) - g) <= tol * np.linalg.norm(total)
+    ok = (not scaled) and np.linalg.norm(a.astype(np.float64) - g) <= tol * np.linalg.norm(total)
+    if ok:
+        ESCAPES["absolute"] += 1
+    return ok
 
 
 def test_golden_fixtures():
     from cvmatrix_b200 import CVMatrix
 
     n_mats = n_stats = n_err = 0
+    for k in ESCAPES:
+        ESCAPES[k] = 0
     for name in golden_io.case_names():
         spec, inp, fit, out = golden_io.case(name)
         dt = np.dtype(spec["dtype"]).type
@@ -88,6 +103,11 @@ def test_golden_fixtures():
                     assert _mat_ok(a, g, fit[m_name], tol, scaled), (name, key, m_name, rel_fro(a, g))
                     n_mats += 1
     assert n_mats > 1500 and n_stats > 2000 and n_err > 50
+    # how many of the matrix checks needed an escape: no golden matrix is non-finite, and only the few unscaled,
+    # centred, nearly-all-rows-held-out float32 cases sit on the absolute cancellation floor
+    print("golden matrix checks:", dict(ESCAPES))
+    assert ESCAPES["checked"] == n_mats and ESCAPES["nonfinite"] == 0
+    assert ESCAPES["absolute"] <= MAX_ABSOLUTE_ESCAPES, ESCAPES
 
 
 def test_partitioner_golden_and_csr():
@@ -132,6 +152,10 @@ def test_midsize_multi_tile_vs_oracle(dtype, weighted):
 
     orc = OracleCVMatrix(dtype=dtype)
     orc.fit(X, Y, w)
+    o64 = None
+    if dtype == np.float32:
+        o64 = OracleCVMatrix(dtype=np.float64)
+        o64.fit(X.astype(np.float64), Y.astype(np.float64), None if w is None else w.astype(np.float64))
     m = CVMatrix(dtype=dtype)
     m.fit(X, Y, w)
     tol = TOL[np.dtype(dtype).name]
@@ -153,17 +177,21 @@ def test_midsize_multi_tile_vs_oracle(dtype, weighted):
         if dtype == np.float64:
             assert rel_fro(XTX, r.XTX) <= tol and rel_fro(XTY, r.XTY) <= tol, (key, rel_fro(XTX, r.XTX), rel_fro(XTY, r.XTY))
         else:
-            # numpy-float32 itself is only accurate to ~1e-4 on centred matrices at this N (SURVEY.md
-            # Appendix B); compare against the float64 evaluation of the same float32 inputs instead
-            pass
+            # numpy-float32 itself is only accurate to ~1e-4 .. 1e-2 on centred matrices at this N (SURVEY.md Appendix
+            # B), so 1e-5 against it is not a meaningful bar here.  Held instead: (a) we are at least as close to the
+            # float64 evaluation of the same float32 inputs as the reference's float32 backend is, and (b) we sit
+            # inside the reference's own error band around it.
+            t64 = o64.fold(val)
+            for got, ref32, truth in ((XTX, r.XTX, t64.XTX), (XTY, r.XTY, t64.XTY)):
+                e_ref, e_us = rel_fro(ref32, truth), rel_fro(got, truth)
+                assert e_us <= 1.5 * e_ref + 1e-5, (key, e_us, e_ref)
+                assert rel_fro(got, ref32) <= 2.5 * e_ref + 1e-5, (key, rel_fro(got, ref32), e_ref)
         assert np.array_equal(XTX, XTX.T)
         # the batched launch and the per-call launch agree bit for bit (same kernels, same split plan
         # for a single fold is not guaranteed -> compare to tolerance)
         assert rel_fro(batch["XTX"][pos], XTX) <= 1e-13 and rel_fro(batch["XTY"][pos], XTY) <= 1e-13
         assert np.array_equal(batch["X_mean"][pos], stats[0]) and np.array_equal(batch["Y_std"][pos], stats[3])
     if dtype == np.float32:
-        o64 = OracleCVMatrix(dtype=np.float64)
-        o64.fit(X.astype(np.float64), Y.astype(np.float64), None if w is None else w.astype(np.float64))
         key = list(part.folds_dict)[1]
         val = part.get_validation_indices(key)
         (XTX, XTY), _ = m.training_XTX_XTY(val)
@@ -466,3 +494,46 @@ def test_cuda_path_equals_naive_recomputation():
                 np.testing.assert_allclose(out["X_std"][f], n["X_std"], atol=1e-10)
             if out["Y_mean"] is not None:
                 np.testing.assert_allclose(out["Y_mean"][f], n["Y_mean"], atol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("K,M", [(130, 4), (97, 3), (33, 0)])
+def test_loo_both_forms_all_flag_combinations(dtype, K, M):
+    """Leave-one-out batches in the streaming form (default) and the exact form (cvmx_set_loo_mode): all 16 flag
+    combinations, even and odd K (16-byte vs scalar stores), no Y, weights with zeros, every `want` selection.
+    Statistics bit-exact in both forms; matrices to the dtype tolerance; XTX exactly symmetric."""
+    import itertools
+
+    from cvmatrix_b200 import CVMatrix, Partitioner
+
+    N = 700
+    X, Y, w, _ = make_inputs(N, K, max(M, 1), 1, seed=K, dtype=dtype)
+    w[::7] = 0
+    Yin = Y[:, :M] if M else None
+    tol = TOL[np.dtype(dtype).name]
+    part = Partitioner(np.arange(N))
+    folds = [0, 1, 6, 7, 350, N - 1]
+    for flags in itertools.product((False, True), repeat=4):
+        orc = OracleCVMatrix(*flags, dtype=dtype)
+        orc.fit(X, Yin, w)
+        m = CVMatrix(*flags, dtype=dtype)
+        m.fit(X, Yin, w)
+        m.set_folds(part)
+        scaled = flags[2] or flags[3]
+        for mode in (0, 1):
+            m.set_loo_mode(mode)
+            out = m.training_batch(return_XTY=bool(M))
+            for f in folds:
+                r = orc.fold(np.array([f]), want_XTY=bool(M))
+                assert _mat_ok(out["XTX"][f], r.XTX, m.XTX, tol, scaled), (flags, mode, f, rel_fro(out["XTX"][f], r.XTX))
+                assert np.array_equal(out["XTX"][f], out["XTX"][f].T)
+                if M:
+                    assert _mat_ok(out["XTY"][f], r.XTY, m.XTY, tol, scaled), (flags, mode, f, rel_fro(out["XTY"][f], r.XTY))
+                for name, g in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
+                    if out[name] is not None and g is not None:
+                        assert np.array_equal(out[name][f], g, equal_nan=True), (flags, mode, f, name)
+            if M:   # single-matrix requests take the same kernels with a narrower `want`
+                only_xx = m.training_batch(0, 8, return_XTY=False)
+                only_xy = m.training_batch(0, 8, return_XTX=False)
+                assert only_xx["XTY"] is None and only_xy["XTX"] is None
+                assert np.array_equal(only_xx["XTX"], out["XTX"][:8]) and np.array_equal(only_xy["XTY"], out["XTY"][:8])
