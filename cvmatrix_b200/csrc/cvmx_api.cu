@@ -97,7 +97,9 @@ struct cvmx_handle {
   bool filling = false;
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
-  DevBuf scan_seg, scan_ok, scan_list, scan_cnt;
+  DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look;
+  int scan_fused = 1;   // passes 1 - 3 in one read of the rows (k_scan_fused); 0: the four-pass form (CVMX_SCAN_FUSED=0)
+  bool attr_scan = false;
   int64_t scan_launches = 0;
   int64_t launches = 0;
   // optional per-kernel timing (cvmx_profile_*): event pairs recorded on the handle stream
@@ -299,12 +301,12 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
     if (loo && h->loo_mode == 0) {
       // streaming form: operand rows of every fold, then 32 x 128 output tiles streamed over the folds
       const int64_t pos0 = off[f0 + c0], ld = h->ld;
-      CU(h, h->loo_ops.reserve((size_t)nf * 4 * ld * sizeof(T)));
-      k_loo_operands<T><<<dim3((unsigned)((ld + 127) / 128), (unsigned)nf), 128, 0, h->stream>>>(
-          h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<T>());
+      CU(h, h->loo_ops.reserve((size_t)nf * 4 * ld * sizeof(double)));
+      k_loo_operands<T><<<dim3((unsigned)nf, (unsigned)((ld + 127) / 128)), 128, 0, h->stream>>>(
+          h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<double>());
       const int col_tiles = (int)((h->K + h->M + LOO_TC - 1) / LOO_TC), row_tiles = (int)((h->K + LOO_TR - 1) / LOO_TR);
       k_loo_tiles<T><<<dim3((unsigned)(col_tiles * row_tiles), (unsigned)((nf + LOO_FOLDS - 1) / LOO_FOLDS)), LOO_THREADS, 0, h->stream>>>(
-          h->Ttot.as<T>(), h->loo_ops.as<T>(), ld, h->K, h->M, col_tiles, nf, want, q.epi.out_xx, q.epi.xx_pitch, q.epi.xx_stride,
+          h->Ttot.as<T>(), h->loo_ops.as<double>(), ld, h->K, h->M, col_tiles, nf, want, q.epi.out_xx, q.epi.xx_pitch, q.epi.xx_stride,
           q.epi.out_xy, q.epi.xy_pitch, q.epi.xy_stride);
       h->launches++;
     } else if (loo) {
@@ -358,7 +360,7 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     const double bytes = ctas * (double)max_rows * MOM_COLS * sizeof(double);
     const double waves = std::ceil(ctas / (3.0 * h->sm_count));
     const double pipe_ns = std::max(7.6 * (double)max_rows * waves, bytes / 6000.0);
-    const double scan_ns = 2.0 * bytes / 5000.0 + 150e3;
+    const double scan_ns = h->scan_fused ? bytes / 5000.0 + 110e3 : 2.0 * bytes / 5000.0 + 150e3;   // fused: one read of the rows
     scan = seg_bytes <= ((size_t)2 << 30) &&
            (h->scan_mode == 2 ? max_rows >= 4 * SCAN_L : (max_rows >= 8192 && scan_ns < pipe_ns && pipe_ns > 0.7 * overlap_ns));
   }
@@ -390,11 +392,33 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
         sp.slow_list = h->scan_list.as<int>(); sp.slow_cnt = h->scan_cnt.as<int>();
         // (measured: capping the streaming grids to a few SMs' worth of CTAs and fatter chain CTAs while a Gram kernel
         // owns the GPU does not change the step time - the passes cost the same SM time either way)
+        if (h->scan_fused) {
+          // one read of the rows: look-back workspace [agg | inc | status | ticket], status and ticket zeroed per launch
+          ScanLook lk;
+          lk.nseq = (int)(mine * ny); lk.mine = (int)mine;
+          const size_t vals = (size_t)lk.nseq * max_segs * 96 * sizeof(double);
+          const size_t flags = ((size_t)lk.nseq * max_segs + 1) * sizeof(int);
+          CU(h, h->scan_look.reserve(2 * vals + flags));
+          lk.agg = h->scan_look.as<double>();
+          lk.inc = lk.agg + (size_t)lk.nseq * max_segs * 96;
+          lk.status = reinterpret_cast<int*>(h->scan_look.as<char>() + 2 * vals);
+          lk.ticket = reinterpret_cast<unsigned*>(lk.status + (size_t)lk.nseq * max_segs);
+          CU(h, cudaMemsetAsync(lk.status, 0, flags, h->stream));
+          if (!h->attr_scan) {
+            CU(h, cudaFuncSetAttribute(k_scan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_fused_smem()));
+            h->attr_scan = true;
+          }
+          const int64_t nsegs = (max_rows + SCAN_L - 1) / SCAN_L;
+          k_scan_fused<<<(unsigned)(lk.nseq * nsegs), SF_THREADS, scan_fused_smem(), h->stream>>>(sp, lk);
+          k_scan_lists<<<dim3((unsigned)((mine * SCAN_COLS * 2 + 3) / 4), ny), 128, 0, h->stream>>>(sp, (int)mine);
+          h->launches -= 1;
+        } else {
         const int64_t quads = (max_segs + SCAN_WARPS - 1) / SCAN_WARPS;
         const dim3 gseg((unsigned)mine, (unsigned)quads, ny);
         k_scan_segsums<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
         k_scan_prefix<<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp);
         k_scan_delta<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+        }
         k_scan_chain<2><<<dim3((unsigned)(mine * (SCAN_COLS / 2)), ny), 64 * 2, scan_chain_smem<2>(), h->stream>>>(sp);
         h->launches += 4; h->scan_launches += 1;
         q.scan_ok = sp.ok; q.scan_groups = sp.groups_total;
@@ -1338,6 +1362,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_SCAN_FUSED")) h->scan_fused = std::atoi(e) ? 1 : 0;
   DeviceGuard guard__(device);
   if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;
@@ -1366,7 +1391,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   if (!h) return CVMX_OK;
   DeviceGuard guard__(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+  for (DevBuf* b : {&h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();

@@ -794,97 +794,132 @@ __global__ void __launch_bounds__(STHREADS, 3) k_loo_folds(const SmallParams<T> 
 // ------------------------------------------------------------------------------------------------------
 constexpr int LOO_TR = 32, LOO_TC = 128, LOO_FOLDS = 32, LOO_THREADS = 256;
 
+// operand rows are float64 for both model dtypes: a float32 model then rounds ONCE, on the final store (its own
+// float32 evaluation of T - G loses ~1e-5 of the centred result to cancellation)
 template <typename T>
 __global__ void __launch_bounds__(128) k_loo_operands(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t K, int64_t M,
                                                       const int64_t* __restrict__ rows, const T* __restrict__ stats,
-                                                      const FoldScalars* __restrict__ fs, uint32_t flags, T* __restrict__ opnd) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t f = blockIdx.y;
+                                                      const FoldScalars* __restrict__ fs, uint32_t flags, double* __restrict__ opnd) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t f = blockIdx.x;
   if (c >= ld) return;
-  T* o = opnd + (size_t)f * 4 * ld;
-  if (c >= K + M) { o[c] = T(0); o[ld + c] = T(0); o[2 * ld + c] = T(1); o[3 * ld + c] = T(0); return; }
+  double* o = opnd + (size_t)f * 4 * ld;
+  if (c >= K + M) { o[c] = 0.0; o[ld + c] = 0.0; o[2 * ld + c] = 1.0; o[3 * ld + c] = 0.0; return; }
   const bool cX = flags & 1, cY = flags & 2, sX = flags & 4, sY = flags & 8;
   const bool isX = c < K;
   const int64_t row = rows[f];
-  const T mean = stats[(size_t)f * 2 * ld + c], sd = stats[(size_t)f * 2 * ld + ld + c];
-  const T rsw = Rn<T>::sqrt((T)fs[f].sw);
-  o[c] = Rn<T>::mul(Rn<T>::sqrt(w[row]), Z[row * ld + c]);
-  const T um = Rn<T>::mul(rsw, mean);
-  o[ld + c] = (isX ? cX : (cX || cY)) ? um : T(0);          // column side
-  o[2 * ld + c] = (isX ? sX : sY) ? Rn<T>::div(T(1), sd) : T(1);
-  o[3 * ld + c] = (isX && (cX || cY)) ? um : T(0);          // row side (X columns only)
+  const double mean = (double)stats[(size_t)f * 2 * ld + c], sd = (double)stats[(size_t)f * 2 * ld + ld + c];
+  const double rsw = __dsqrt_rn(fs[f].sw);
+  o[c] = __dmul_rn(__dsqrt_rn((double)w[row]), (double)Z[row * ld + c]);
+  const double um = __dmul_rn(rsw, mean);
+  o[ld + c] = (isX ? cX : (cX || cY)) ? um : 0.0;            // column side
+  o[2 * ld + c] = (isX ? sX : sY) ? __ddiv_rn(1.0, sd) : 1.0;
+  o[3 * ld + c] = (isX && (cX || cY)) ? um : 0.0;            // row side (X columns only)
 }
 
-template <typename T> struct Vec4;
-template <> struct Vec4<double> { double v[4]; __device__ __forceinline__ void load(const double* p) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; } };
-template <> struct Vec4<float> { float v[4]; __device__ __forceinline__ void load(const float* p) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; } };
+struct Dbl4 {
+  double v[4];
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
+
+// Column map of a lane inside a 128-column tile.  float64: two column PAIRS 64 columns apart, so that each of the two
+// 16-byte stores of a row is contiguous across the warp (512 bytes, whole sectors; four consecutive columns per lane
+// would leave every 32-byte sector half-written by each instruction).  float32: four consecutive columns, one 16-byte store.
+template <typename T> struct LooMap;
+template <> struct LooMap<double> {
+  static __device__ __forceinline__ int col(int lane, int b) { return (b < 2 ? 0 : 64) + 2 * lane + (b & 1); }
+  static __device__ __forceinline__ void load(const double* base, int lane, double (&v)[4]) {   // base: column 0 of the tile
+    const double2 a = __ldg(reinterpret_cast<const double2*>(base + 2 * lane)), b = __ldg(reinterpret_cast<const double2*>(base + 64 + 2 * lane));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(double* base, int lane, const double (&o)[4], bool second) {
+    *reinterpret_cast<double2*>(base + 2 * lane) = make_double2(o[0], o[1]);
+    if (second) *reinterpret_cast<double2*>(base + 64 + 2 * lane) = make_double2(o[2], o[3]);
+  }
+  static constexpr int FIRST = 2;     // columns b < FIRST belong to the first store
+};
+template <> struct LooMap<float> {
+  static __device__ __forceinline__ int col(int lane, int b) { return 4 * lane + b; }
+  static __device__ __forceinline__ void load(const double* base, int lane, double (&v)[4]) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(base + 4 * lane)), b = __ldg(reinterpret_cast<const double2*>(base + 4 * lane + 2));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(float* base, int lane, const double (&o)[4], bool) {
+    *reinterpret_cast<float4*>(base + 4 * lane) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+  }
+  static constexpr int FIRST = 4;
+};
 
 template <typename T>
-__global__ void __launch_bounds__(LOO_THREADS, 2) k_loo_tiles(const T* __restrict__ Ttot, const T* __restrict__ opnd, int64_t ld, int64_t K,
+__global__ void __launch_bounds__(LOO_THREADS, 2) k_loo_tiles(const T* __restrict__ Ttot, const double* __restrict__ opnd, int64_t ld, int64_t K,
                                                               int64_t M, int col_tiles, int64_t nfolds, uint32_t want,
                                                               T* __restrict__ out_xx, int64_t xx_pitch, int64_t xx_stride,
                                                               T* __restrict__ out_xy, int64_t xy_pitch, int64_t xy_stride) {
-  typedef typename GramCfg<T>::vec2 vec2;
+  typedef LooMap<T> Map;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles;
-  const int64_t i0 = (int64_t)rt * LOO_TR + 4 * warp, j0 = (int64_t)ct * LOO_TC + 4 * lane;
+  const int64_t i0 = (int64_t)rt * LOO_TR + 4 * warp, jt = (int64_t)ct * LOO_TC;    // first row of the thread, first column of the tile
   const int64_t C = K + M;
   const int64_t fbeg = (int64_t)blockIdx.y * LOO_FOLDS;
   const int nf = (int)(min(nfolds, fbeg + LOO_FOLDS) - fbeg);
   const bool wxx = want & 1, wxy = want & 2;
-  if (i0 >= K || j0 >= C) return;
-  if (!((wxx && j0 < K) || (wxy && j0 + 3 >= K))) return;
+  if (i0 >= K || jt >= C) return;
+  if (!((wxx && jt < K) || (wxy && jt + LOO_TC > K))) return;
   const int nr = (int)min((int64_t)4, K - i0);                       // live rows of this thread
-  // 16-byte stores need an even element offset on every row (j0 is a multiple of 4)
-  const bool fast = wxx && j0 + 3 < K && (xx_pitch % 2 == 0) && (xx_stride % 2 == 0) &&
-                    (reinterpret_cast<uintptr_t>(out_xx) % (2 * sizeof(T)) == 0);
+#define LOO_JC(b) (jt + Map::col(lane, (b)))
+  // 16-byte stores: the lane's columns of a store all inside XTX, 16-byte aligned element offsets on every row
+  constexpr int VEC = 16 / sizeof(T);
+  const bool aligned = wxx && (xx_pitch % VEC == 0) && (xx_stride % VEC == 0) && (reinterpret_cast<uintptr_t>(out_xx) % 16 == 0);
+  const bool fast1 = aligned && LOO_JC(Map::FIRST - 1) < K;          // first store (float32: the only one)
+  const bool fast2 = aligned && LOO_JC(3) < K;                       // second store (float64)
+  const bool fast = fast1 && (Map::FIRST == 4 || fast2 || LOO_JC(2) >= C);   // nothing of this lane needs the scalar path
 
-  T tt[4][4];
+  double tt[4][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    Vec4<T> t;
-    t.load(Ttot + min(i0 + a, K - 1) * ld + j0);                     // j0 + 3 < ld (ld % 32 == 0)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) tt[a][b] = t.v[b];
-  }
-  const T* __restrict__ op = opnd + (size_t)fbeg * 4 * ld;
-  T* oxx = out_xx + (size_t)fbeg * xx_stride + i0 * xx_pitch + j0;
+    for (int b = 0; b < 4; ++b) tt[a][b] = (double)__ldg(Ttot + min(i0 + a, K - 1) * ld + min(LOO_JC(b), ld - 1));
+  const double* __restrict__ op = opnd + (size_t)fbeg * 4 * ld;      // tiles never reach past ld: ld % 32 == 0 and ...
+  const bool in_ld = jt + LOO_TC <= ld;                              // ... a partial last tile loads column by column
+  T* oxx = out_xx + (size_t)fbeg * xx_stride + i0 * xx_pitch + jt;
   T* oxy = out_xy + (size_t)fbeg * xy_stride + i0 * xy_pitch;
 
 #pragma unroll 1
   for (int f = 0; f < nf; ++f) {
-    Vec4<T> vj, uj, rj, vi, ui, ri;
-    vj.load(op + j0); uj.load(op + ld + j0); rj.load(op + 2 * ld + j0);
+    double vj[4], uj[4], rj[4];
+    Dbl4 vi, ui, ri;
+    if (in_ld) {
+      Map::load(op + jt, lane, vj); Map::load(op + ld + jt, lane, uj); Map::load(op + 2 * ld + jt, lane, rj);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t j = min(LOO_JC(b), ld - 1);
+        vj[b] = __ldg(op + j); uj[b] = __ldg(op + ld + j); rj[b] = __ldg(op + 2 * ld + j);
+      }
+    }
     vi.load(op + i0); ri.load(op + 2 * ld + i0); ui.load(op + 3 * ld + i0);   // warp-uniform (i0 + 3 < ld)
-    T o[4][4];
+    double o[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b)
-        o[a][b] = Rn<T>::mul(fma(-vi.v[a], vj.v[b], fma(-ui.v[a], uj.v[b], tt[a][b])), Rn<T>::mul(ri.v[a], rj.v[b]));
+        o[a][b] = __dmul_rn(fma(-vi.v[a], vj[b], fma(-ui.v[a], uj[b], tt[a][b])), __dmul_rn(ri.v[a], rj[b]));
     if (fast) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        if (a < nr) {
-          vec2 lo, hi;
-          lo.x = o[a][0]; lo.y = o[a][1]; hi.x = o[a][2]; hi.y = o[a][3];
-          *reinterpret_cast<vec2*>(oxx + a * xx_pitch) = lo;
-          *reinterpret_cast<vec2*>(oxx + a * xx_pitch + 2) = hi;
-        }
-      }
+      for (int a = 0; a < 4; ++a)
+        if (a < nr) Map::store(oxx + a * xx_pitch, lane, o[a], fast2);
     } else {
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         if (a >= nr) continue;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const int64_t jj = j0 + b;
-          if (jj < K) { if (wxx) oxx[a * xx_pitch + b] = o[a][b]; }
-          else if (jj < C && wxy) oxy[a * xy_pitch + (jj - K)] = o[a][b];
+          const int64_t jj = LOO_JC(b);
+          if (jj < K) { if (wxx) oxx[a * xx_pitch + (jj - jt)] = (T)o[a][b]; }
+          else if (jj < C && wxy) oxy[a * xy_pitch + (jj - K)] = (T)o[a][b];
         }
       }
     }
@@ -892,6 +927,7 @@ __global__ void __launch_bounds__(LOO_THREADS, 2) k_loo_tiles(const T* __restric
     oxx += xx_stride;
     oxy += xy_stride;
   }
+#undef LOO_JC
 }
 
 }  // namespace cvmx

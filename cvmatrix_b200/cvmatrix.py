@@ -75,6 +75,11 @@ class CVMatrix:
         backend: str = "numpy",
         device: Optional[int] = None,
     ) -> None:
+        if backend == "jax":
+            # same exception type and install hint as the reference without JAX (cvmatrix/cvmatrix.py:85-90): the JAX
+            # path is the reference package's optional extra; this engine has no multi-backend dispatch
+            raise ImportError("backend='jax' is the reference package's optional JAX path (`pip install cvmatrix[jax]`); "
+                              "cvmatrix_b200 implements the numpy-backend semantics on B200 only.")
         if backend not in ("numpy", "cuda"):
             raise ValueError(f"Invalid backend: {backend!r}. This engine implements the numpy-backend semantics on B200 only.")
         self.center_X = center_X
@@ -513,8 +518,11 @@ class CVMatrix:
             rc = self._lib.cvmx_training_batch(self._h, fold_begin, fold_end, want, p(XTX), p(XTY), p(stats), p(scal), p(status), mem)
             _lib.check(rc, self._h)
         finally:
-            if out == "torch" and bound:   # always unbind: a failed call must not leave the handle on the caller's stream
-                self._lib.cvmx_set_stream(self._h, prev_stream)  # syncs, back to the stream the handle was on
+            if out == "torch":
+                if bound:   # always unbind: a failed call must not leave the handle on the caller's stream
+                    self._lib.cvmx_set_stream(self._h, prev_stream)  # syncs, back to the private stream
+                else:       # legacy default stream: the results must be complete before torch touches them
+                    self._lib.cvmx_sync(self._h)
         if check:
             st = status.cpu().numpy() if out == "torch" else status
             for s in np.unique(st):

@@ -63,8 +63,10 @@ def test_no_cpu_fallback():
 def test_constructor_argument_checks():
     from cvmatrix_b200 import CVMatrix
 
-    with pytest.raises(ValueError, match="Invalid backend"):
+    with pytest.raises(ImportError, match=r"cvmatrix\[jax\]"):   # the reference's exception without JAX (cvmatrix.py:85-90)
         CVMatrix(backend="jax")
+    with pytest.raises(ValueError, match="Invalid backend"):
+        CVMatrix(backend="torch")
     with pytest.raises(TypeError):
         CVMatrix(dtype=np.float16)
 

@@ -513,22 +513,37 @@ def test_loo_both_forms_all_flag_combinations(dtype, K, M):
     tol = TOL[np.dtype(dtype).name]
     part = Partitioner(np.arange(N))
     folds = [0, 1, 6, 7, 350, N - 1]
+    f32 = dtype == np.float32
     for flags in itertools.product((False, True), repeat=4):
         orc = OracleCVMatrix(*flags, dtype=dtype)
         orc.fit(X, Yin, w)
+        o64 = None
+        if f32:
+            o64 = OracleCVMatrix(*flags, dtype=np.float64)
+            o64.fit(X.astype(np.float64), None if Yin is None else Yin.astype(np.float64), w.astype(np.float64))
         m = CVMatrix(*flags, dtype=dtype)
         m.fit(X, Yin, w)
         m.set_folds(part)
         scaled = flags[2] or flags[3]
+
+        def ok(got, ref, truth, total, mode):
+            if f32 and mode == 0:
+                # the streaming form evaluates a float32 model in float64 and rounds once: it is closer to the float64
+                # evaluation than numpy-float32 is, and sits inside numpy-float32's own error band around it
+                e_ref, e_us = rel_fro(ref, truth), rel_fro(got, truth)
+                return e_us <= 1.5 * e_ref + 1e-6 and rel_fro(got, ref) <= 2.5 * e_ref + 1e-5
+            return _mat_ok(got, ref, total, tol, scaled)
+
         for mode in (0, 1):
             m.set_loo_mode(mode)
             out = m.training_batch(return_XTY=bool(M))
             for f in folds:
                 r = orc.fold(np.array([f]), want_XTY=bool(M))
-                assert _mat_ok(out["XTX"][f], r.XTX, m.XTX, tol, scaled), (flags, mode, f, rel_fro(out["XTX"][f], r.XTX))
+                t = o64.fold(np.array([f]), want_XTY=bool(M)) if f32 else r
+                assert ok(out["XTX"][f], r.XTX, t.XTX, m.XTX, mode), (flags, mode, f, rel_fro(out["XTX"][f], r.XTX))
                 assert np.array_equal(out["XTX"][f], out["XTX"][f].T)
                 if M:
-                    assert _mat_ok(out["XTY"][f], r.XTY, m.XTY, tol, scaled), (flags, mode, f, rel_fro(out["XTY"][f], r.XTY))
+                    assert ok(out["XTY"][f], r.XTY, t.XTY, m.XTY, mode), (flags, mode, f, rel_fro(out["XTY"][f], r.XTY))
                 for name, g in (("X_mean", r.X_mean), ("X_std", r.X_std), ("Y_mean", r.Y_mean), ("Y_std", r.Y_std)):
                     if out[name] is not None and g is not None:
                         assert np.array_equal(out[name][f], g, equal_nan=True), (flags, mode, f, name)

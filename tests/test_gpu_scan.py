@@ -69,8 +69,12 @@ def test_scan_equals_chain_and_oracle_friendly(weighted):
             assert _same(got, want)
 
 
-def test_scan_adversarial_columns_bit_exact():
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_scan_adversarial_columns_bit_exact(fused, monkeypatch):
+    """fused = "1": passes 1 - 3 in one read of the rows (k_scan_fused, decoupled look-back); "0": the four-pass form."""
     from cvmatrix_b200 import CVMatrix
+
+    monkeypatch.setenv("CVMX_SCAN_FUSED", fused)   # read by cvmx_create
 
     N = 60_000
     A = _adversarial(N)
