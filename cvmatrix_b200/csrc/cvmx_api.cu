@@ -93,6 +93,12 @@ struct cvmx_handle {
   TableCache tc_gram, tc_finish;
   DevBuf fold_gram, fold_raw, chunk_ranges;   // fold_raw: [P][2][ld] raw column sums of every fold, same validity
   int64_t fold_gram_version = -1;
+  // row-slab mode (cvmx_fit_end_slab): this handle holds rows [row0, row0 + N) of an N_glob-row data set; the weight
+  // vector and the validation sets are ALSO kept in global form for the (pairwise, unsplittable) weight sums
+  bool slab = false;
+  int64_t N_glob = 0, row0 = 0;
+  DevBuf w_glob, g_off, g_idx;
+  std::vector<int64_t> g_h_off;
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
   bool filling = false;
   int64_t fill_units_cap = 0, fill_calls = 0;
@@ -409,7 +415,9 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
             h->attr_scan = true;
           }
           const int64_t nsegs = (max_rows + SCAN_L - 1) / SCAN_L;
-          k_scan_fused<<<(unsigned)(lk.nseq * nsegs), SF_THREADS, scan_fused_smem(), h->stream>>>(sp, lk);
+          lk.total = (unsigned)(lk.nseq * nsegs);
+          const unsigned ctas = (unsigned)std::min<int64_t>((int64_t)lk.total, (int64_t)3 * h->sm_count);   // persistent: 3 per SM
+          k_scan_fused<<<ctas, SF_THREADS, scan_fused_smem(), h->stream>>>(sp, lk);
           k_scan_lists<<<dim3((unsigned)((mine * SCAN_COLS * 2 + 3) / 4), ny), 128, 0, h->stream>>>(sp, (int)mine);
           h->launches -= 1;
         } else {
@@ -466,15 +474,23 @@ int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx,
   // weight masses on side stream 2 (ordered after the memsets above)
   CU(h, cudaEventRecord(h->ev_mass, h->stream));
   CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+  // row-slab mode: the weight sums run over the GLOBAL weight vector and validation sets (numpy's pairwise tree cannot
+  // be cut at slab boundaries); K, M >= 2 there, so the kernel never touches Z
+  const T* wm_w = h->slab ? h->w_glob.as<T>() : h->w.as<T>();
+  const int64_t* wm_off = h->slab ? h->g_off.as<int64_t>() : d_off;
+  const int64_t* wm_idx = h->slab ? h->g_idx.as<int64_t>() : d_idx;
+  const int64_t wm_N = h->slab ? h->N_glob : h->N;
+  int64_t wm_rows = max_rows;
+  if (h->slab) for (int64_t f = f0; f < f0 + Pn; ++f) wm_rows = std::max(wm_rows, h->g_h_off[f + 1] - h->g_h_off[f]);
   for (int64_t c0 = 0; c0 < Pn; c0 += 0x7fffffff) {
     const int64_t nb = std::min<int64_t>(0x7fffffff, Pn - c0);
-    if (max_rows <= 1024)
+    if (wm_rows <= 1024)
       k_weight_mass<T, PW_LEVELS_SMALL><<<(unsigned)nb, 1 << PW_LEVELS_SMALL, 0, h->aux2_stream>>>(
-          h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
+          h->Z.as<T>(), wm_w, ld, wm_N, h->K, h->M, h->weighted ? 1 : 0, wm_off, wm_idx, f0 + c0, 0, h->ddof,
           h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
     else
       k_weight_mass<T, PW_LEVELS_BIG><<<(unsigned)nb, 1 << PW_LEVELS_BIG, 0, h->aux2_stream>>>(
-          h->Z.as<T>(), h->w.as<T>(), ld, h->N, h->K, h->M, h->weighted ? 1 : 0, d_off, d_idx, f0 + c0, 0, h->ddof,
+          h->Z.as<T>(), wm_w, ld, wm_N, h->K, h->M, h->weighted ? 1 : 0, wm_off, wm_idx, f0 + c0, 0, h->ddof,
           h->fit_scal.as<FitScalars>(), h->fscal.as<FoldScalars>() + c0, h->pwcols.as<T>() + 4 * c0);
     h->launches++;
   }
@@ -532,7 +548,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
                  const void* w, int32_t mem, int64_t g0, int64_t g1, const FoldFuse* ff = nullptr) {
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
-  h->fitted = false; h->filling = false;
+  h->fitted = false; h->filling = false; h->slab = false;
   h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = w != nullptr;
   h->P = 0; h->csr_version++; h->plan = Plan();
   CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
@@ -828,7 +844,7 @@ template <typename T>
 int32_t fit_begin_impl(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weighted, int64_t max_block_rows) {
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
-  h->fitted = false; h->filling = false;
+  h->fitted = false; h->filling = false; h->slab = false;
   h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = weighted != 0;
   h->P = 0; h->csr_version++; h->plan = Plan();
   CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
@@ -943,9 +959,23 @@ int32_t fit_rows_impl(cvmx_t* h, int64_t row0, int64_t nr, const void* X, int64_
   return CVMX_OK;
 }
 
+struct SlabArgs { const void* carry_sum; const void* carry_sumsq; const void* w_glob; int64_t N_glob; int64_t row0; };
+
 template <typename T>
-int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
+int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const SlabArgs* sl = nullptr) {
   const int64_t N = h->N, K = h->K, M = h->M, ld = h->ld;
+  if (sl) {
+    // row-slab mode: the weight sums need every weight of the data set, the moment chains continue the previous slab's
+    if (h->weighted) {
+      CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(sl->N_glob, 1) * sizeof(T)));
+      CU(h, cudaMemcpyAsync(h->w_glob.p, sl->w_glob, (size_t)sl->N_glob * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (sl->carry_sum) {
+      CU(h, cudaMemcpyAsync(h->sum_z.p, sl->carry_sum, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+      CU(h, cudaMemcpyAsync(h->sumsq_z.p, sl->carry_sumsq, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->slab = true; h->N_glob = sl->N_glob; h->row0 = sl->row0;
+  }
   // accumulator -> totals (raw epilogue: mirrored XtWX, XtWY)
   std::vector<int2> tiles;
   plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), tiles);
@@ -967,8 +997,9 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
   h->launches++;
   CU(h, cudaGetLastError());
   // statistics over all rows: weight mass everywhere, moment sums for this column shard (others stay zero)
-  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), h->w.as<T>(), ld, N, K, M, h->weighted ? 1 : 0, nullptr,
-                                                                          nullptr, 0, 1, h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), sl && h->weighted ? h->w_glob.as<T>() : h->w.as<T>(), ld,
+                                                                          sl ? sl->N_glob : N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
+                                                                          h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
   h->launches++;
   MomentParams<T> mp;
   mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
@@ -976,6 +1007,7 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards) {
   mp.flags = h->flags; mp.resolution = (T)h->resolution;
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
+  mp.accumulate = (sl && sl->carry_sum) ? 1 : 0;
   int32_t rc = launch_moments<T>(h, mp, 1, N, col_shard, n_col_shards, 0.0);
   if (rc) return rc;
   FitScalars fsc;
@@ -1152,7 +1184,9 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
     // units: split each fold's shard so the grid fills the SMs in whole waves
     const int64_t sms = h->sm_count;
     int64_t best_R = 4096; double best = -1;
-    for (int64_t R = 1024; R <= 4096; R += GBK) {
+    // wide K: the tiles alone fill the GPU in many waves - one unit per fold shard, no partial workspace to sum
+    if (nt >= sms) { best_R = INT64_MAX / 4; best = 2; }
+    for (int64_t R = 1024; R <= 4096 && best < 2; R += GBK) {
       int64_t items = 0;
       for (int64_t f = 0; f < Pn; ++f) items += std::max<int64_t>(1, (off2[2 * f + 1] - off2[2 * f] + R - 1) / R);
       items *= nt;
@@ -1178,11 +1212,12 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
     if (rcu) return rcu;
   }
   const int ntiles = tc.ntiles;
-  CU(h, h->partials.reserve((size_t)tc.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
+  const bool direct = tc.n_partial_units == Pn;     // one unit per fold: k_gram writes the fold's raw Gram itself
+  if (!direct) CU(h, h->partials.reserve((size_t)tc.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
   GramParams<T> gp;
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = h->d_idx.as<int64_t>();
   gp.units = tc.units.as<GramUnit>(); gp.tiles = tc.tiles.as<int2>(); gp.ntiles = ntiles;
-  gp.partials = h->partials.as<double>(); gp.raw_out = out; gp.force_partials = 1;
+  gp.partials = direct ? out : h->partials.as<double>(); gp.raw_out = out; gp.force_partials = 1;
   gp.epi = EpiParams<T>();
   const size_t smem = gram_smem_bytes<T>();
   if (!h->attr_gram) {
@@ -1195,9 +1230,15 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
-  k_partial_sum<<<dim3((unsigned)(GACC * GTHREADS / 512), (unsigned)ntiles, (unsigned)Pn), 256, 0, h->stream>>>(
-      h->partials.as<double>(), tc.units.as<GramUnit>(), tc.fold_units.as<int32_t>(), ntiles, out);
-  h->launches++;
+  if (!direct) {
+    for (int64_t t0 = 0; t0 < ntiles; t0 += 65535) {   // grid.y limit
+      const unsigned ty = (unsigned)std::min<int64_t>(65535, ntiles - t0);
+      k_partial_sum<<<dim3((unsigned)(GACC * GTHREADS / 512), ty, (unsigned)Pn), 256, 0, h->stream>>>(
+          h->partials.as<double>() + (size_t)t0 * GACC * GTHREADS, tc.units.as<GramUnit>(), tc.fold_units.as<int32_t>(), ntiles,
+          out + (size_t)t0 * GACC * GTHREADS);
+    }
+    h->launches++;
+  }
   prof_span(h, PROF_REDUCE, ev1, prof_mark(h));
   CU(h, cudaGetLastError());
   return CVMX_OK;
@@ -1335,6 +1376,31 @@ int32_t upload_csr(cvmx_t* h, DevBuf& doff, DevBuf& didx, const int64_t* offsets
   return CVMX_OK;
 }
 
+template <typename T>
+int32_t slab_fold_sums(cvmx_t* h, int64_t f0, int64_t f1, void* carry) {
+  const int64_t Pn = f1 - f0, ld = h->ld;
+  std::vector<int64_t> ranges(2 * Pn);
+  int64_t max_rows = 0;
+  for (int64_t f = 0; f < Pn; ++f) {
+    ranges[2 * f] = h->h_off[f0 + f]; ranges[2 * f + 1] = h->h_off[f0 + f + 1];
+    max_rows = std::max(max_rows, ranges[2 * f + 1] - ranges[2 * f]);
+  }
+  CU(h, h->chunk_ranges.reserve(ranges.size() * sizeof(int64_t)));
+  CU(h, cudaMemcpyAsync(h->chunk_ranges.p, ranges.data(), ranges.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));   // `ranges` is a local
+  MomentParams<T> fc;
+  fc.Z = h->Z.as<T>(); fc.w = h->w.as<T>(); fc.ld = ld; fc.K = h->K; fc.M = h->M;
+  fc.offsets = nullptr; fc.indices = h->d_idx.as<int64_t>(); fc.fold0 = 0; fc.N = h->N;
+  fc.flags = h->flags; fc.resolution = (T)h->resolution;
+  fc.sum_z = h->sum_z.as<T>(); fc.sumsq_z = h->sumsq_z.as<T>();
+  fc.fs = nullptr; fc.pw_cols = nullptr; fc.stats = nullptr;
+  fc.ranges = h->chunk_ranges.as<int64_t>(); fc.raw = (T*)carry; fc.accumulate = 1;
+  const int ev0 = prof_mark(h);
+  int32_t rc = launch_moments<T>(h, fc, Pn, max_rows);
+  prof_span(h, PROF_STATS, ev0, prof_mark(h));
+  return rc;
+}
+
 }  // namespace
 
 // ---- C ABI -------------------------------------------------------------------------------------------
@@ -1391,7 +1457,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   if (!h) return CVMX_OK;
   DeviceGuard guard__(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+  for (DevBuf* b : {&h->w_glob, &h->g_off, &h->g_idx, &h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
@@ -1667,12 +1733,14 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
   if (h->dtype != CVMX_F64) return fail(h, CVMX_ERR_INVALID, "cvmx_sharded_finish_peers: float64 handles only");
   ON_DEVICE(h);
   // statistics rows of the whole batch: sum of the peers' column shards, straight into the statistics buffer
-  const int64_t nst = (batch_f1 - batch_f0) * 2 * h->ld;
-  PeerList pl8;
-  for (int q = 0; q < 8; ++q) pl8.p[q] = q < n_peers ? (const double*)peer_bufs[q] : nullptr;
-  k_peer_sum_rows<double><<<(unsigned)((nst + 255) / 256), 256, 0, h->stream>>>(pl8, n_peers, gram_count, nst, h->stats.as<double>());
-  h->launches++;
-  CU(h, cudaGetLastError());
+  if (gram_count >= 0) {   // (negative: the handle's own statistics are already complete - row-slab mode)
+    const int64_t nst = (batch_f1 - batch_f0) * 2 * h->ld;
+    PeerList pl8;
+    for (int q = 0; q < 8; ++q) pl8.p[q] = q < n_peers ? (const double*)peer_bufs[q] : nullptr;
+    k_peer_sum_rows<double><<<(unsigned)((nst + 255) / 256), 256, 0, h->stream>>>(pl8, n_peers, gram_count, nst, h->stats.as<double>());
+    h->launches++;
+    CU(h, cudaGetLastError());
+  }
   int32_t rc = sharded_finish<double>(h, batch_f0, f0, f1, want, (const double*)peer_bufs[0], (double*)oxx, (double*)oxy,
                                       (const double* const*)peer_bufs, n_peers);
   if (rc || f1 == f0) return rc;
@@ -1689,6 +1757,50 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
   return CVMX_OK;
 }
 
+
+
+// ---- row-slab mode: this handle holds rows [row0, row0 + N) of an N_glob-row data set -------------------------------
+int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_sumsq, const void* w_glob, int64_t N_glob, int64_t row0) {
+  if (!h || !h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end_slab: call cvmx_fit_begin first");
+  if (N_glob < h->N || row0 < 0 || row0 + h->N > N_glob || (h->weighted && !w_glob) || ((carry_sum == nullptr) != (carry_sumsq == nullptr)))
+    return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end_slab: bad slab arguments");
+  if (h->K < 2 || h->M == 1)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_fit_end_slab: row slabs need K >= 2 and M != 1 (single columns are summed pairwise over all rows)");
+  ON_DEVICE(h);
+  SlabArgs sl{carry_sum, carry_sumsq, w_glob, N_glob, row0};
+  return h->dtype == CVMX_F64 ? fit_end_impl<double>(h, 0, 1, &sl) : fit_end_impl<float>(h, 0, 1, &sl);
+}
+
+int32_t cvmx_set_weight_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P) {
+  if (!h || !h->fitted || !h->slab) return fail(h, CVMX_ERR_INVALID, "cvmx_set_weight_folds: fit a row slab first (cvmx_fit_end_slab)");
+  if (!offsets || P != h->P || (offsets[P] > 0 && !indices)) return fail(h, CVMX_ERR_INVALID, "cvmx_set_weight_folds: one global index set per fold of cvmx_set_folds");
+  ON_DEVICE(h);
+  h->g_h_off.assign(offsets, offsets + P + 1);
+  const int64_t N_local = h->N;
+  h->N = h->N_glob;   // upload_csr normalises against h->N
+  int32_t rc = upload_csr(h, h->g_off, h->g_idx, offsets, indices, P, offsets[P], CVMX_HOST);
+  h->N = N_local;
+  return rc;
+}
+
+int32_t cvmx_slab_fold_sums(cvmx_t* h, int64_t f0, int64_t f1, void* carry) {
+  if (!h || !h->fitted || !h->slab) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_fold_sums: fit a row slab first (cvmx_fit_end_slab)");
+  if (f0 < 0 || f1 > h->P || f0 >= f1 || !carry) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_fold_sums: bad fold range or buffer");
+  ON_DEVICE(h);
+  return h->dtype == CVMX_F64 ? slab_fold_sums<double>(h, f0, f1, carry) : slab_fold_sums<float>(h, f0, f1, carry);
+}
+
+int32_t cvmx_slab_finalize_stats(cvmx_t* h, int64_t f0, int64_t f1, const void* raw) {
+  if (!h || !h->fitted || !h->slab) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_finalize_stats: fit a row slab first (cvmx_fit_end_slab)");
+  if (f0 < 0 || f1 > h->P || f0 >= f1 || !raw || (int64_t)h->g_h_off.size() != h->P + 1)
+    return fail(h, CVMX_ERR_INVALID, "cvmx_slab_finalize_stats: bad fold range / buffer, or cvmx_set_weight_folds not called");
+  ON_DEVICE(h);
+  int64_t max_rows = 0;
+  for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, h->h_off[f + 1] - h->h_off[f]);
+  return h->dtype == CVMX_F64
+             ? launch_fold_stats<double>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, f1 - f0, max_rows, 0, 1, 0.0, (const double*)raw)
+             : launch_fold_stats<float>(h, h->d_off.as<int64_t>(), h->d_idx.as<int64_t>(), f0, f1 - f0, max_rows, 0, 1, 0.0, (const float*)raw);
+}
 
 int32_t cvmx_validation_rows(cvmx_t* h, int64_t fold, const void* stats, uint32_t apply, void* out_X, void* out_Y, int32_t mem) {
   if (!h || !h->fitted) return fail(h, CVMX_ERR_INVALID, "cvmx_validation_rows: fit first");

@@ -34,7 +34,7 @@ namespace cvmx {
 
 constexpr int SCAN_COLS = MOM_COLS;   // same column groups as k_moments_pipe (column sharding is per group)
 constexpr int SCAN_WARPS = 4;         // segments per CTA in the two streaming passes
-constexpr int SCAN_L = 256;           // rows per segment (multiple of 32; compile-time in pass 4)
+constexpr int SCAN_L = 128;           // rows per segment (multiple of 32; compile-time in pass 4 and in k_scan_fused)
 
 struct ScanParams {
   MomentParams<double> p;
@@ -370,16 +370,20 @@ __global__ void __launch_bounds__(64 * SCAN_CHAIN_COLS) k_scan_chain(ScanParams 
 // ---- passes 1 - 3 in ONE read of the rows (decoupled look-back) ----------------------------------------------------
 // The four-pass form reads every row twice (pass 1 and pass 3), and that second read is what the scan costs beside a
 // Gram kernel that owns the tensor pipe but not the memory system.  k_scan_fused stages one segment (SCAN_L rows x 32
-// columns = 64 KB) in shared memory ONCE and does everything that needs the rows from there:
+// columns) in shared memory ONCE and does everything that needs the rows from there:
 //   1. segment sums S, A, Q (any order) from shared memory;
 //   2. the prefix over all earlier segments of the same (fold, column group) by decoupled look-back (Merrill & Garland):
 //      the CTA publishes its aggregate, then a warp polls the status words of up to 32 predecessors at a time
 //      (lane = predecessor), adds their aggregates down to the nearest published inclusive prefix (lane = column) and
-//      publishes its own inclusive prefix.  CTAs take their work in ticket order (an atomic counter: a CTA only ever
-//      waits for tickets smaller than its own, which are already running), tickets are dealt round-robin over the
-//      (fold, group) sequences so that every sequence advances together;
+//      publishes its own inclusive prefix;
 //   3. the proxy starts (same interval test as k_scan_prefix) and the four proxy chains per column (2 sums x 2 parities,
 //      one warp each) - again from shared memory.
+// CTAs are persistent and take (sequence, segment) tasks in ticket order from an atomic counter, dealt round-robin over
+// the (fold, group) sequences so that every sequence advances together; a CTA only ever waits for tickets smaller
+// than its own, and the smallest unfinished ticket is always being processed, so look-back cannot deadlock.  Every
+// CTA prefetches the rows of its NEXT task (cp.async into the other half of a double buffer) before it starts on the
+// current one: without that, look-back couples each task to its 32 predecessors and the whole GPU falls into
+// lock-step load / compute phases (measured: 2 TB/s; the first version of this kernel).
 // Slow segments are marked in the d0 plane with a reserved NaN payload (a fast segment's increments are finite);
 // k_scan_lists turns the marks into the ascending per-column lists k_scan_chain walks.  The approximate prefix now
 // depends on the order in which look-back happened to add the aggregates; that only moves segments between "fast" and
@@ -394,17 +398,18 @@ struct ScanLook {
   unsigned* ticket;   // work counter (zeroed with the status words before every launch)
   int nseq;           // sequences = folds x own column groups
   int mine;           // own column groups per fold
+  unsigned total;     // tasks = nseq x segments of the longest fold
 };
 
 constexpr size_t scan_fused_smem() {
-  return (size_t)SCAN_L * SCAN_COLS * sizeof(double)      // rows of the segment
-         + (size_t)SCAN_L * sizeof(double)                // their weights
-         + 3072                                           // row numbers (2 KB), later the cross-warp sums [4][3][32]
+  return 2 * ((size_t)SCAN_L * SCAN_COLS * sizeof(double) + (size_t)SCAN_L * sizeof(double))   // two segments + their weights
+         + 3072                                           // row numbers, later the cross-warp sums [4][3][32]
          + 3 * 32 * sizeof(double)                        // exclusive prefix
          + 3 * 32 * sizeof(double)                        // segment sums
          + 2 * 32 * sizeof(double)                        // proxy starts
          + 64;
 }
+static_assert(SCAN_L * 8 <= 3072 && SCAN_L % 32 == 0, "row-number scratch");
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -415,45 +420,64 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+struct ScanTask {       // one (sequence, segment)
+  int seq; int g; int cnt; bool valid;
+  int64_t seg, f, c0, n, r0;
+  const int64_t* idx;
+};
+
 __global__ void __launch_bounds__(SF_THREADS, 3) k_scan_fused(ScanParams sp, ScanLook lk) {
   extern __shared__ __align__(128) unsigned char sf_smem[];
   const MomentParams<double>& p = sp.p;
-  double* tile = reinterpret_cast<double*>(sf_smem);                       // [SCAN_L][32]
-  double* swt = tile + (size_t)SCAN_L * SCAN_COLS;                         // [SCAN_L]
-  long long* srow = reinterpret_cast<long long*>(swt + SCAN_L);            // [SCAN_L]   (dead after the copies are issued)
+  double* tile0 = reinterpret_cast<double*>(sf_smem);                      // [2][SCAN_L][32]
+  double* swt0 = tile0 + (size_t)2 * SCAN_L * SCAN_COLS;                   // [2][SCAN_L]
+  long long* srow = reinterpret_cast<long long*>(swt0 + 2 * SCAN_L);       // [SCAN_L]   (only while copies are issued)
   double* red = reinterpret_cast<double*>(srow);                           // [4][3][32] (aliases srow)
   double* ex = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srow) + 3072);   // [3][32]
   double* segs = ex + 96;                                                  // [3][32]
   double* prox = segs + 96;                                                // [2][32]
-  unsigned* misc = reinterpret_cast<unsigned*>(prox + 64);                 // [0] ticket, [1] negative-square flag
+  unsigned* misc = reinterpret_cast<unsigned*>(prox + 64);                 // [0] ticket, [1] negative-square flags
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) { misc[0] = atomicAdd(lk.ticket, 1u); misc[1] = 0u; }
-  __syncthreads();
-  const unsigned ticket = misc[0];
-  const int seq = (int)(ticket % (unsigned)lk.nseq);
-  const int64_t seg = (int64_t)(ticket / (unsigned)lk.nseq);
-  const int64_t f = seq / lk.mine;
-  const int g = p.grp0 + (seq % lk.mine) * p.grp_stride;
-  const int64_t c0 = (int64_t)g * SCAN_COLS;
-  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
-  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
-  const int64_t* idx = p.offsets ? p.indices + beg : nullptr;
-  if (seg == 0 && tid == 0) sp.ok[f * sp.groups_total + g] = 1;            // k_scan_lists may clear it
-  const int64_t r0 = seg * SCAN_L;
-  if (r0 >= n) return;
-  const int cnt = (int)min((int64_t)SCAN_L, n - r0);
-
-  // ---- stage the segment: row numbers and weights first, then 16-byte chunks (16 lanes cover one 256-byte row piece)
-  for (int r = tid; r < SCAN_L; r += SF_THREADS) {
-    const long long row = r < cnt ? (idx ? idx[r0 + r] : p.row0 + r0 + r) : -1;
-    srow[r] = row;
-    cp_async8(swt + r, p.w + (row >= 0 ? row : 0), row >= 0 ? 8 : 0);
-  }
-  __syncthreads();
-  {
+  // next valid task in ticket order (tasks past the end of a short fold are skipped); block-uniform
+  auto take = [&]() -> ScanTask {
+    ScanTask t;
+    t.valid = false;
+    while (true) {
+      __syncthreads();
+      if (tid == 0) misc[0] = atomicAdd(lk.ticket, 1u);
+      __syncthreads();
+      const unsigned ticket = misc[0];
+      if (ticket >= lk.total) return t;
+      t.seq = (int)(ticket % (unsigned)lk.nseq);
+      t.seg = (int64_t)(ticket / (unsigned)lk.nseq);
+      t.f = t.seq / lk.mine;
+      t.g = p.grp0 + (t.seq % lk.mine) * p.grp_stride;
+      t.c0 = (int64_t)t.g * SCAN_COLS;
+      const int64_t beg = p.offsets ? p.offsets[p.fold0 + t.f] : 0;
+      t.n = p.offsets ? p.offsets[p.fold0 + t.f + 1] - beg : p.N;
+      t.idx = p.offsets ? p.indices + beg : nullptr;
+      if (t.seg == 0 && tid == 0) sp.ok[t.f * sp.groups_total + t.g] = 1;  // k_scan_lists may clear it
+      t.r0 = t.seg * SCAN_L;
+      if (t.r0 >= t.n) continue;
+      t.cnt = (int)min((int64_t)SCAN_L, t.n - t.r0);
+      t.valid = true;
+      return t;
+    }
+  };
+  // stage the rows of a task: row numbers and weights first, then 16-byte chunks (16 lanes cover one 256-byte row piece)
+  auto issue = [&](const ScanTask& t, int buf) {
+    double* tile = tile0 + (size_t)buf * SCAN_L * SCAN_COLS;
+    double* swt = swt0 + buf * SCAN_L;
+    __syncthreads();                                       // srow / red free again
+    for (int r = tid; r < SCAN_L; r += SF_THREADS) {
+      const long long row = r < t.cnt ? (t.idx ? t.idx[t.r0 + r] : p.row0 + t.r0 + r) : -1;
+      srow[r] = row;
+      cp_async8(swt + r, p.w + (row >= 0 ? row : 0), row >= 0 ? 8 : 0);
+    }
+    __syncthreads();
     const int chunk = tid & 15, rr = tid >> 4;
-    const char* zbase = reinterpret_cast<const char*>(p.Z + c0 + chunk * 2);
+    const char* zbase = reinterpret_cast<const char*>(p.Z + t.c0 + chunk * 2);
     const long long row_bytes = (long long)p.ld * 8;
 #pragma unroll 8
     for (int k = 0; k < SCAN_L / 8; ++k) {
@@ -461,160 +485,175 @@ __global__ void __launch_bounds__(SF_THREADS, 3) k_scan_fused(ScanParams sp, Sca
       const long long row = srow[r];
       cp_async16(tile + (size_t)r * SCAN_COLS + chunk * 2, zbase + (row >= 0 ? row : 0) * row_bytes, row >= 0 ? 16 : 0);
     }
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
+    cp_async_commit();
+  };
 
-  // ---- 1. segment sums (rows past the end are zero-filled: t = q = +0) ---------------------------------------------
-  {
-    double S[4] = {0, 0, 0, 0}, A[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
-    unsigned neg = 0;
-    const double* zt = tile + (size_t)(warp * (SCAN_L / 4)) * SCAN_COLS + lane;
-    const double* wt = swt + warp * (SCAN_L / 4);
+  ScanTask cur = take();
+  int buf = 0;
+  if (cur.valid) issue(cur, buf);
+  while (cur.valid) {
+    ScanTask nxt = take();
+    if (nxt.valid) { issue(nxt, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const double* tile = tile0 + (size_t)buf * SCAN_L * SCAN_COLS;
+    const double* swt = swt0 + buf * SCAN_L;
+    const int seq = cur.seq, cnt = cur.cnt;
+    const int64_t seg = cur.seg, f = cur.f, c0 = cur.c0;
+    if (tid == 0) misc[1] = 0u;
+
+    // ---- 1. segment sums (rows past the end are zero-filled: t = q = +0) -------------------------------------------
+    {
+      double S[4] = {0, 0, 0, 0}, A[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
+      unsigned neg = 0;
+      const double* zt = tile + (size_t)(warp * (SCAN_L / 4)) * SCAN_COLS + lane;
+      const double* wt = swt + warp * (SCAN_L / 4);
 #pragma unroll 4
-    for (int r = 0; r < SCAN_L / 4; r += 4) {
+      for (int r = 0; r < SCAN_L / 4; r += 4) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double z = zt[(size_t)(r + u) * SCAN_COLS];
-        const double t = __dmul_rn(z, wt[r + u]);
-        const double q = __dmul_rn(t, z);
-        S[u] = __dadd_rn(S[u], t);
-        A[u] = __dadd_rn(A[u], fabs(t));
-        Q[u] = __dadd_rn(Q[u], fabs(q));
-        neg |= (unsigned)(__double2hiint(q) & 0x80000000);
+        for (int u = 0; u < 4; ++u) {
+          const double z = zt[(size_t)(r + u) * SCAN_COLS];
+          const double t = __dmul_rn(z, wt[r + u]);
+          const double q = __dmul_rn(t, z);
+          S[u] = __dadd_rn(S[u], t);
+          A[u] = __dadd_rn(A[u], fabs(t));
+          Q[u] = __dadd_rn(Q[u], fabs(q));
+          neg |= (unsigned)(__double2hiint(q) & 0x80000000);
+        }
       }
+      __syncthreads();                                     // misc[1] cleared
+      red[(warp * 3 + 0) * 32 + lane] = (S[0] + S[1]) + (S[2] + S[3]);
+      red[(warp * 3 + 1) * 32 + lane] = (A[0] + A[1]) + (A[2] + A[3]);
+      red[(warp * 3 + 2) * 32 + lane] = (Q[0] + Q[1]) + (Q[2] + Q[3]);
+      if (neg) atomicOr(&misc[1], 1u << lane);
     }
-    red[(warp * 3 + 0) * 32 + lane] = (S[0] + S[1]) + (S[2] + S[3]);
-    red[(warp * 3 + 1) * 32 + lane] = (A[0] + A[1]) + (A[2] + A[3]);
-    red[(warp * 3 + 2) * 32 + lane] = (Q[0] + Q[1]) + (Q[2] + Q[3]);
-    if (neg) atomicOr(&misc[1], 1u << lane);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- 2. look-back (warp 0; lane = column for values, lane = predecessor for status words) ------------------------
-  if (warp == 0) {
-    double a[3];
+    // ---- 2. look-back (warp 0; lane = column for values, lane = predecessor for status words) ----------------------
+    if (warp == 0) {
+      double a[3];
 #pragma unroll
-    for (int v = 0; v < 3; ++v) a[v] = (red[(0 * 3 + v) * 32 + lane] + red[(1 * 3 + v) * 32 + lane]) + (red[(2 * 3 + v) * 32 + lane] + red[(3 * 3 + v) * 32 + lane]);
-    // q = rn(rn(w z) z) is non-negative unless a weight is negative (fit rejects those): then the squares chain is never fast
-    if ((misc[1] >> lane) & 1u) a[2] = __longlong_as_double(0x7ff8000000000000LL);
-    const int64_t c = c0 + lane;
-    const size_t base = ((size_t)seq * sp.max_segs) * 96;
-    double* myagg = lk.agg + base + (size_t)seg * 96;
-    double* myinc = lk.inc + base + (size_t)seg * 96;
-    int* st = lk.status + (size_t)seq * sp.max_segs;
-    double e[3] = {0.0, 0.0, 0.0};
-    if (seg == 0) {
-      if (p.accumulate && c < p.K + p.M) { e[0] = p.sum_z[c]; e[2] = p.sumsq_z[c]; }   // chunked fit: the chains continue
-    } else {
+      for (int v = 0; v < 3; ++v) a[v] = (red[(0 * 3 + v) * 32 + lane] + red[(1 * 3 + v) * 32 + lane]) + (red[(2 * 3 + v) * 32 + lane] + red[(3 * 3 + v) * 32 + lane]);
+      // q = rn(rn(w z) z) is non-negative unless a weight is negative (fit rejects those): then the squares chain is never fast
+      if ((misc[1] >> lane) & 1u) a[2] = __longlong_as_double(0x7ff8000000000000LL);
+      const int64_t c = c0 + lane;
+      const size_t base = ((size_t)seq * sp.max_segs) * 96;
+      double* myagg = lk.agg + base + (size_t)seg * 96;
+      double* myinc = lk.inc + base + (size_t)seg * 96;
+      int* st = lk.status + (size_t)seq * sp.max_segs;
+      double e[3] = {0.0, 0.0, 0.0};
+      if (seg == 0) {
+        if (p.accumulate && c < p.K + p.M) { e[0] = p.sum_z[c]; e[2] = p.sumsq_z[c]; }   // chunked fit: the chains continue
+      } else {
 #pragma unroll
-      for (int v = 0; v < 3; ++v) __stcg(myagg + v * 32 + lane, a[v]);
+        for (int v = 0; v < 3; ++v) __stcg(myagg + v * 32 + lane, a[v]);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(st + seg, 1);
+        int64_t j = seg - 1;                     // nearest predecessor not yet added
+        unsigned long long spins = 0;
+        while (true) {
+          const int64_t pj = j - lane;
+          const int s = pj >= 0 ? ld_acquire_gpu(st + pj) : 3;
+          const unsigned has_inc = __ballot_sync(0xffffffffu, s == 2);
+          const int stop = has_inc ? __ffs(has_inc) - 1 : 32;              // predecessors j .. j - stop (the last one inclusive)
+          const unsigned need = stop >= 31 ? 0xffffffffu : ((2u << stop) - 1u);
+          const unsigned ready = __ballot_sync(0xffffffffu, s != 0);
+          if ((ready & need) != need) {
+            if (++spins > (1ull << 24)) __trap();                          // a lost predecessor must not hang the GPU
+            __nanosleep(40);
+            continue;
+          }
+          __threadfence();
+          const int last = has_inc ? stop : 31;
+          for (int k0 = 0; k0 <= last; k0 += 8) {
+            double v[8][3];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int k = k0 + u;
+              const bool on = k <= last && j - k >= 0;
+              const double* src = ((has_inc && k == stop) ? lk.inc : lk.agg) + base + (size_t)(on ? j - k : 0) * 96;
+#pragma unroll
+              for (int w3 = 0; w3 < 3; ++w3) v[u][w3] = on ? __ldcg(src + w3 * 32 + lane) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+              for (int w3 = 0; w3 < 3; ++w3) e[w3] += v[u][w3];
+          }
+          if (has_inc) break;
+          j -= 32;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 3; ++v) { ex[v * 32 + lane] = e[v]; segs[v * 32 + lane] = a[v]; __stcg(myinc + v * 32 + lane, e[v] + a[v]); }
       __threadfence();
       __syncwarp();
-      if (lane == 0) st_release_gpu(st + seg, 1);
-      int64_t j = seg - 1;                     // nearest predecessor not yet added
-      unsigned long long spins = 0;
-      while (true) {
-        const int64_t pj = j - lane;
-        const int s = pj >= 0 ? ld_acquire_gpu(st + pj) : 3;
-        const unsigned has_inc = __ballot_sync(0xffffffffu, s == 2);
-        const int stop = has_inc ? __ffs(has_inc) - 1 : 32;              // predecessors j .. j - stop (the last one inclusive)
-        const unsigned need = stop >= 32 ? 0xffffffffu : ((2u << stop) - 1u);
-        const unsigned ready = __ballot_sync(0xffffffffu, s != 0);
-        if ((ready & need) != need) {
-          if (++spins > (1ull << 24)) __trap();                          // a lost predecessor must not hang the GPU
-          __nanosleep(64);
-          continue;
-        }
-        __threadfence();
-        const int last = has_inc ? stop : 31;
-        for (int k0 = 0; k0 <= last; k0 += 8) {
-          double v[8][3];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u;
-            const bool on = k <= last && j - k >= 0;
-            const double* src = ((has_inc && k == stop) ? lk.inc : lk.agg) + base + (size_t)(on ? j - k : 0) * 96;
-#pragma unroll
-            for (int w3 = 0; w3 < 3; ++w3) v[u][w3] = on ? __ldcg(src + w3 * 32 + lane) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int w3 = 0; w3 < 3; ++w3) e[w3] += v[u][w3];
-        }
-        if (has_inc) break;
-        j -= 32;
-      }
+      if (lane == 0) st_release_gpu(st + seg, 2);
     }
-#pragma unroll
-    for (int v = 0; v < 3; ++v) { ex[v * 32 + lane] = e[v]; segs[v * 32 + lane] = a[v]; __stcg(myinc + v * 32 + lane, e[v] + a[v]); }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) st_release_gpu(st + seg, 2);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- 3a. proxy starts (threads 0..63: chain = warp, column = lane; same test as k_scan_prefix) --------------------
-  if (warp < 2) {
-    const int chain = warp;
-    const double Pj = chain == 0 ? ex[lane] : ex[64 + lane];
-    const double totj = chain == 0 ? ex[32 + lane] : ex[64 + lane];
-    const double Aj = chain == 0 ? segs[32 + lane] : segs[64 + lane];
-    const double A1 = Aj * (1.0 + 0x1p-20);
-    const double margin = 0x1p-24 * fabs(totj) + 0x1p-40 * fabs(Pj);
-    const double lo = (Pj - A1) - margin, hi = (Pj + A1) + margin;
-    const long long blo = __double_as_longlong(lo), bhi = __double_as_longlong(hi);
-    const int elo = (int)((blo >> 52) & 0x7ff), ehi = (int)((bhi >> 52) & 0x7ff);
-    const bool same = ((blo ^ bhi) >= 0) && elo == ehi && elo >= 1 && elo <= 2046;
-    double B = 0.0;
-    if (Aj == 0.0) B = -0.0;                                                          // only zeros: s + (+-0)
-    else if (same) B = __longlong_as_double((blo & (long long)0xfff0000000000000ULL) | 0x0008000000000000LL);
-    if (c0 + lane >= p.K + p.M) B = 0.0;
-    prox[chain * 32 + lane] = B;
-  }
-  __syncthreads();
+    // ---- 3a. proxy starts (threads 0..63: chain = warp, column = lane; same test as k_scan_prefix) ------------------
+    if (warp < 2) {
+      const int chain = warp;
+      const double Pj = chain == 0 ? ex[lane] : ex[64 + lane];
+      const double totj = chain == 0 ? ex[32 + lane] : ex[64 + lane];
+      const double Aj = chain == 0 ? segs[32 + lane] : segs[64 + lane];
+      const double A1 = Aj * (1.0 + 0x1p-20);
+      const double margin = 0x1p-24 * fabs(totj) + 0x1p-40 * fabs(Pj);
+      const double lo = (Pj - A1) - margin, hi = (Pj + A1) + margin;
+      const long long blo = __double_as_longlong(lo), bhi = __double_as_longlong(hi);
+      const int elo = (int)((blo >> 52) & 0x7ff), ehi = (int)((bhi >> 52) & 0x7ff);
+      const bool same = ((blo ^ bhi) >= 0) && elo == ehi && elo >= 1 && elo <= 2046;
+      double B = 0.0;
+      if (Aj == 0.0) B = -0.0;                                                          // only zeros: s + (+-0)
+      else if (same) B = __longlong_as_double((blo & (long long)0xfff0000000000000ULL) | 0x0008000000000000LL);
+      if (c0 + lane >= p.K + p.M) B = 0.0;
+      prox[chain * 32 + lane] = B;
+    }
+    __syncthreads();
 
-  // ---- 3b. proxy chains from shared memory: warp = (chain, parity), lane = column ----------------------------------
-  {
-    const int chain = warp >> 1, parity = warp & 1;
-    const double B = prox[chain * 32 + lane];
-    const long long bb = __double_as_longlong(B);
-    const bool slow = bb == 0;
-    const bool ident = bb == (long long)0x8000000000000000ULL;
-    const double start = (parity && !ident) ? __longlong_as_double(bb | 1) : B;
-    double acc = start;
-    const double* zt = tile + lane;
-    if (!__all_sync(0xffffffffu, slow)) {
-      if (cnt == SCAN_L) {
+    // ---- 3b. proxy chains from shared memory: warp = (chain, parity), lane = column --------------------------------
+    {
+      const int chain = warp >> 1, parity = warp & 1;
+      const double B = prox[chain * 32 + lane];
+      const long long bb = __double_as_longlong(B);
+      const bool slow = bb == 0;
+      const bool ident = bb == (long long)0x8000000000000000ULL;
+      const double start = (parity && !ident) ? __longlong_as_double(bb | 1) : B;
+      double acc = start;
+      const double* zt = tile + lane;
+      if (!__all_sync(0xffffffffu, slow)) {
+        if (cnt == SCAN_L) {
 #pragma unroll 2
-        for (int r = 0; r < SCAN_L; r += 8) {
-          double t[8];
+          for (int r = 0; r < SCAN_L; r += 8) {
+            double t[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const double z = zt[(size_t)(r + u) * SCAN_COLS];
-            t[u] = __dmul_rn(z, swt[r + u]);
-            if (chain) t[u] = __dmul_rn(t[u], z);
+            for (int u = 0; u < 8; ++u) {
+              const double z = zt[(size_t)(r + u) * SCAN_COLS];
+              t[u] = __dmul_rn(z, swt[r + u]);
+              if (chain) t[u] = __dmul_rn(t[u], z);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t[u]);
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t[u]);
-        }
-      } else {
-        for (int r = 0; r < cnt; ++r) {
-          const double z = zt[(size_t)r * SCAN_COLS];
-          double t = __dmul_rn(z, swt[r]);
-          if (chain) t = __dmul_rn(t, z);
-          acc = __dadd_rn(acc, t);
+        } else {
+          for (int r = 0; r < cnt; ++r) {
+            const double z = zt[(size_t)r * SCAN_COLS];
+            double t = __dmul_rn(z, swt[r]);
+            if (chain) t = __dmul_rn(t, z);
+            acc = __dadd_rn(acc, t);
+          }
         }
       }
+      const int64_t c = c0 + lane;
+      if (c < p.K + p.M) {
+        double d = ident ? acc : __dsub_rn(acc, start);
+        if (slow) d = __longlong_as_double((long long)SCAN_SLOW_MARK);
+        scan_plane(sp, f, chain, parity, c)[seg] = d;
+      }
     }
-    const int64_t c = c0 + lane;
-    if (c < p.K + p.M) {
-      double d = ident ? acc : __dsub_rn(acc, start);
-      if (slow) d = __longlong_as_double((long long)SCAN_SLOW_MARK);
-      scan_plane(sp, f, chain, parity, c)[seg] = d;
-    }
+    cur = nxt;
+    buf ^= 1;
   }
 }
 

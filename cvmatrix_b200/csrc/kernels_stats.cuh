@@ -190,6 +190,7 @@ k_weight_mass(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int6
     fit->sum_w = weighted ? (double)swv : (double)N;
     fit->nnz_w = weighted ? (int64_t)s_cnt[0] : N;
     fit->neg_weight = s_cnt[1] != 0;
+    fit->pad = 0;
     return;
   }
   T sw, nz;

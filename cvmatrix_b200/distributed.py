@@ -236,3 +236,177 @@ def fit_sharded_upload(cvm: CVMatrix, X, Y=None, weights=None, group=None, block
     cvm._pull_totals()
     cvm.X, cvm.Y = X, Y
     cvm.weights = None if w is None else w.reshape(-1, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Row-slab mode (BASELINE config 5): the ROWS of the data set are sharded across the ranks instead of replicated.
+# ---------------------------------------------------------------------------------------------------------------------
+class RowSlabFolds:
+    """
+    A data set whose rows are sharded across the ranks of ``group`` (rank r holds rows ``sharding.slab_rows(r, world, N)``):
+    fit and fold batches with every reduction over rows cut at the slab boundaries (include/cvmx.h, "Row-slab mode").
+
+        rs = RowSlabFolds(cvm, N, K, M, weights_global)     # cvm: a fresh CVMatrix on this rank's device
+        rs.fit(blocks)                                       # blocks: iterable of (global_row0, X_block, Y_block) inside the slab
+        rs.set_folds(partitioner)                            # validation sets as GLOBAL row numbers
+        out = rs.training_batch()                            # device tensors for the folds this rank owns
+
+    * Gram totals: per-slab partial, one NCCL all-reduce (K x ld elements).
+    * Fold Grams: per-slab partials in symmetric memory, summed by the fold owner over NVLink inside the epilogue kernel
+      (no collective); NCCL all-reduce fallback when symmetric memory is unavailable or the model is float32.
+    * numpy-order column sums (sequential over rows): chained rank to rank - a rank continues the running sums it
+      receives and hands them on (2 x ld values per fold per hop), the last rank broadcasts the result.
+    * weight sums (pairwise trees over all rows): every rank holds the whole weight vector and evaluates them itself.
+    """
+
+    def __init__(self, cvm: CVMatrix, N: int, K: int, M: int, weights=None, group=None, block_rows: int = 65536):
+        import torch
+        import torch.distributed as dist
+
+        self.cvm, self.group, self.dist, self.torch = cvm, group, dist, torch
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dev = torch.device("cuda", cvm.device)
+        self.f64 = np.dtype(cvm.dtype) == np.float64
+        self.tdt = torch.float64 if self.f64 else torch.float32
+        self.N, self.K, self.M = int(N), int(K), int(M or 0)
+        self.row0, self.row1 = sharding.slab_rows(self.rank, self.world, self.N)
+        self.block_rows = int(block_rows)
+        self.w_host = None
+        if weights is not None and not hasattr(weights, "data_ptr"):
+            self.w_host = np.ascontiguousarray(np.asarray(weights, dtype=cvm.dtype).reshape(-1))
+            weights = torch.from_numpy(self.w_host).to(self.dev)
+        self.w = weights                     # all N weights, on the device (None: unweighted)
+        self.use_peers = self.world > 1 and self.world <= 8 and self.f64
+        self._symm = None
+        self._step = 0
+        self._gram = None
+        self.P = 0
+
+    def _grank(self, r: int) -> int:
+        return self.dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def fit(self, blocks) -> None:
+        t, dist, cvm = self.torch, self.dist, self.cvm
+        lib, h = cvm._lib, cvm._h
+        n_local = self.row1 - self.row0
+        cvm.fit_begin(n_local, self.K, self.M, weighted=self.w is not None, max_block_rows=self.block_rows)
+        for b0, Xb, Yb in blocks:
+            nb = int(Xb.shape[0])
+            if b0 < self.row0 or b0 + nb > self.row1:
+                raise ValueError("block outside this rank's row slab")
+            wb = None
+            if self.w is not None:
+                if hasattr(Xb, "is_cuda") and Xb.is_cuda:
+                    wb = self.w[b0:b0 + nb]
+                else:                                    # host blocks take host weights
+                    if self.w_host is None:
+                        self.w_host = self.w.cpu().numpy()
+                    wb = self.w_host[b0:b0 + nb]
+            cvm.fit_rows(b0 - self.row0, Xb, Yb if self.M else None, wb, gram=True)
+        ld = int(lib.cvmx_ld(h))
+        carry = t.zeros((2, ld), dtype=self.tdt, device=self.dev)
+        if self.world > 1 and self.rank > 0:
+            dist.recv(carry, src=self._grank(self.rank - 1), group=self.group)
+            t.cuda.current_stream(self.dev).synchronize()
+        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
+        first = self.rank == 0
+        _lib.check(lib.cvmx_fit_end_slab(h, None if first else vp(carry[0]), None if first else vp(carry[1]), vp(self.w), self.N, self.row0), h)
+        sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_moments_ptr(h, C.byref(sp), C.byref(qp), C.byref(mc)), h)
+        ts = "<f8" if self.f64 else "<f4"
+        sum_z = t.as_tensor(_DevArray(sp.value, ld, ts), device=self.dev)
+        sumsq_z = t.as_tensor(_DevArray(qp.value, ld, ts), device=self.dev)
+        if self.world > 1:
+            carry[0].copy_(sum_z)
+            carry[1].copy_(sumsq_z)
+            if self.rank < self.world - 1:
+                dist.send(carry, dst=self._grank(self.rank + 1), group=self.group)
+            dist.broadcast(carry, src=self._grank(self.world - 1), group=self.group)   # the last slab's chains are the totals
+            sum_z.copy_(carry[0])
+            sumsq_z.copy_(carry[1])
+            tp, cnt, ldt = C.c_void_p(), C.c_int64(), C.c_int64()
+            _lib.check(lib.cvmx_totals_ptr(h, C.byref(tp), C.byref(cnt), C.byref(ldt)), h)
+            dist.all_reduce(t.as_tensor(_DevArray(tp.value, cnt.value, ts), device=self.dev), group=self.group)
+            t.cuda.current_stream(self.dev).synchronize()
+            _lib.check(lib.cvmx_commit_totals(h), h)
+        cvm._streamed = True
+        cvm.N = self.N
+        cvm._pull_totals()
+
+    def set_folds(self, folds) -> None:
+        from .partitioner import Partitioner
+
+        cvm = self.cvm
+        if isinstance(folds, Partitioner):
+            offsets, indices = folds.csr()
+        else:
+            offsets, indices = folds
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        loc_off, loc_idx = sharding.local_csr(offsets, indices, self.row0, self.row1)
+        cvm._upload_csr(loc_off, loc_idx)
+        _lib.check(cvm._lib.cvmx_set_weight_folds(cvm._h, offsets.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+                                                  offsets.size - 1), cvm._h)
+        self.P = offsets.size - 1
+
+    def alloc_outputs(self, n_folds: int):
+        t, K, M = self.torch, self.K, self.M
+        return dict(
+            XTX=t.empty((n_folds, K, K), dtype=self.tdt, device=self.dev),
+            XTY=t.empty((n_folds, K, M), dtype=self.tdt, device=self.dev) if M else None,
+            stats=t.empty((n_folds, 2, K + M), dtype=self.tdt, device=self.dev),
+            scal=t.empty((n_folds, 2), dtype=self.tdt, device=self.dev),
+            status=t.empty((n_folds,), dtype=t.int32, device=self.dev),
+        )
+
+    def _setup_symm(self, half_elems: int):
+        return ShardedFolds._setup_symm(self, half_elems)
+
+    def training_batch(self, f0: int = 0, f1: Optional[int] = None, out: Optional[dict] = None):
+        """Folds ``[f0, f1)``; returns device tensors for the folds this rank owns (``sharding.fold_block``).  Call on a
+        non-default torch stream that the handle has been bound to (cvmx_set_stream)."""
+        t, dist, cvm = self.torch, self.dist, self.cvm
+        lib, h = cvm._lib, cvm._h
+        if f1 is None:
+            f1 = self.P
+        o0, o1 = sharding.fold_block(self.rank, self.world, f0, f1)
+        if out is None:
+            out = self.alloc_outputs(max(o1 - o0, 1))
+        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
+        want = _lib.WANT_XTX | (_lib.WANT_XTY if self.M else 0)
+        ld = int(lib.cvmx_ld(h))
+        # 1. the folds' column sums, chained slab to slab in row order
+        carry = t.zeros((f1 - f0, 2, ld), dtype=self.tdt, device=self.dev)
+        if self.world > 1 and self.rank > 0:
+            dist.recv(carry, src=self._grank(self.rank - 1), group=self.group)
+        _lib.check(lib.cvmx_slab_fold_sums(h, f0, f1, vp(carry)), h)
+        if self.world > 1:
+            if self.rank < self.world - 1:
+                dist.send(carry, dst=self._grank(self.rank + 1), group=self.group)
+            dist.broadcast(carry, src=self._grank(self.world - 1), group=self.group)
+        # 2. weight masses (global), means and stds of every fold of the batch, on every rank
+        _lib.check(lib.cvmx_slab_finalize_stats(h, f0, f1, vp(carry)), h)
+        # 3. this slab's raw Gram of every fold, then the owners sum their peers' over NVLink inside the epilogue kernel
+        n = lib.cvmx_sharded_gram_count(h, f0, f1, want)
+        if self.use_peers and (self._symm is None or self._symm[2] < n):
+            self._symm = self._setup_symm(n)
+        if self._symm is not None and self.world > 1:
+            buf, hdl, cap, ptrs = self._symm
+            half = self._step & 1
+            self._step += 1
+            gram = buf[half * cap: half * cap + n]
+            _lib.check(lib.cvmx_sharded_gram(h, f0, f1, want, 0, 1, vp(gram)), h)
+            hdl.barrier(channel=0)
+            _lib.check(lib.cvmx_sharded_finish_peers(h, f0, f1, o0, o1, want, ptrs[half], self.world, -1, vp(out["XTX"]), vp(out["XTY"]),
+                                                     vp(out["stats"]), vp(out["scal"]), vp(out["status"])), h)
+            return dict(out, fold_begin=o0, fold_end=o1)
+        if self._gram is None or self._gram.numel() < n:
+            self._gram = t.empty((n,), dtype=t.float64, device=self.dev)
+        gram = self._gram[:n]
+        _lib.check(lib.cvmx_sharded_gram(h, f0, f1, want, 0, 1, vp(gram)), h)
+        if self.world > 1:
+            dist.all_reduce(gram, group=self.group)
+        _lib.check(lib.cvmx_sharded_finish(h, f0, o0, o1, want, vp(gram), vp(out["XTX"]), vp(out["XTY"]), vp(out["stats"]),
+                                           vp(out["scal"]), vp(out["status"])), h)
+        return dict(out, fold_begin=o0, fold_end=o1)

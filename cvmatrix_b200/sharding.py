@@ -39,3 +39,28 @@ def column_groups(ld: int, shard: int, n_shards: int, group_cols: int = MOMENT_G
     """Column groups (of `group_cols` columns) whose moment chains `shard` computes."""
     n_groups = -(-ld // group_cols)
     return list(range(shard, n_groups, n_shards))
+
+
+def slab_rows(rank: int, world: int, n_rows: int):
+    """Row slab [begin, end) of `rank` when the ROWS of the data set are sharded across ranks (BASELINE config 5)."""
+    return rank * n_rows // world, (rank + 1) * n_rows // world
+
+
+def local_csr(offsets, indices, row0: int, row1: int):
+    """The part of a global CSR of validation sets (ascending row numbers inside every fold) that falls into the row slab
+    [row0, row1), renumbered from 0: (local offsets, local indices).  Raises if a fold is not ascending - the chained
+    column sums rely on a fold's rows on rank r all preceding those on rank r + 1."""
+    import numpy as np
+
+    offsets = np.asarray(offsets, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    P = offsets.size - 1
+    parts, loc = [], np.zeros(P + 1, np.int64)
+    for f in range(P):
+        idx = indices[offsets[f]:offsets[f + 1]]
+        if idx.size > 1 and np.any(np.diff(idx) <= 0):
+            raise ValueError(f"fold {f}: row-slab mode needs strictly ascending validation indices")
+        lo, hi = np.searchsorted(idx, row0), np.searchsorted(idx, row1)
+        parts.append(idx[lo:hi] - row0)
+        loc[f + 1] = loc[f] + (hi - lo)
+    return loc, (np.concatenate(parts) if parts else np.zeros(0, np.int64))

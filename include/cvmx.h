@@ -202,10 +202,43 @@ int32_t cvmx_sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1,
  * memory; peer_bufs[q] = rank q's buffer, this rank's own included, at most 8).  The owner of folds [f0, f1) sums the
  * peers' fragments on the fly inside the epilogue kernel (P2P loads) and the peers' statistics rows for the batch
  * [batch_f0, batch_f1) with a small kernel.  The caller provides the cross-GPU barrier between phase 2 and this call
- * (cvmatrix_b200/distributed.py: symmetric-memory barrier).  float64 handles. */
+ * (cvmatrix_b200/distributed.py: symmetric-memory barrier).  float64 handles.  gram_count < 0: the statistics of the
+ * batch are already complete in this handle (row-slab mode, cvmx_slab_finalize_stats) and only the Grams are summed. */
 int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1, int64_t f0, int64_t f1, uint32_t want,
                                   const void* const* peer_bufs, int32_t n_peers, int64_t gram_count, void* out_XTX,
                                   void* out_XTY, void* out_stats, void* out_scal, int32_t* out_status);
+
+/*
+ * Row-slab mode (BASELINE config 5: N = 2M x K = 5000 float64 is 80 GB - the rows are sharded across the GPUs of a box
+ * instead of replicated).  One handle per rank holds rows [row0, row0 + N_local) of the N_glob-row data set; the same
+ * reference code as cvmx_fit / cvmx_training_batch is replaced (cvmatrix/cvmatrix.py:1209-1243 fit, :589-752 fold
+ * statistics, :1001-1009 kernel matrices), with the row dimension of every reduction cut at the slab boundaries:
+ *   - Gram totals and fold Grams are sums over rows: per-slab partials, reduced across ranks by the caller
+ *     (all-reduce of cvmx_totals_ptr(); cvmx_sharded_gram with row shard 0 of 1 + cvmx_sharded_finish_peers);
+ *   - numpy's column sums are sequential over rows, so they are CHAINED slab to slab: a rank continues the running
+ *     sums it receives from the previous rank and hands them on (carry buffers in the model dtype);
+ *   - numpy's weight sums are pairwise trees over all rows, which cannot be cut: every rank keeps the whole weight
+ *     vector and the global validation index sets (small) and evaluates them itself.
+ * Folds must list their rows in ascending order (a Partitioner always does), so that a fold's rows on rank r all
+ * precede those on rank r + 1.  K >= 2 and M != 1 (a single column is summed pairwise over all rows by numpy).
+ *   cvmx_fit_end_slab        : completes cvmx_fit_begin(N_local, ...) / cvmx_fit_rows.  carry_sum / carry_sumsq: device
+ *                              rows of ld elements (NULL on the first rank) = the moment chains after the previous
+ *                              slab; afterwards cvmx_moments_ptr() holds the chains after THIS slab (send them on; the
+ *                              last rank's are final: write them back into cvmx_moments_ptr() on every rank).  w_glob:
+ *                              device vector of all N_glob weights (NULL when unweighted), copied.  cvmx_totals_ptr()
+ *                              holds this slab's partial [XtWX | XtWY]: all-reduce(sum) it across ranks.
+ *   cvmx_set_folds           : the LOCAL validation sets (rows of this slab, numbered from 0), as usual;
+ *   cvmx_set_weight_folds    : the same folds as GLOBAL row numbers (host arrays), for the weight sums;
+ *   cvmx_slab_fold_sums      : carry [f1 - f0][2][ld] (device, model dtype, in / out): the folds' raw column sums
+ *                              (sum w z, sum w z z) after the previous slab -> after this slab (zeros on the first rank);
+ *   cvmx_slab_finalize_stats : raw = the completed sums of the last rank (same layout) -> weight masses, means, stds of
+ *                              folds [f0, f1) in the handle's statistics buffer, ready for cvmx_sharded_finish_peers
+ *                              (called with gram_count < 0: no statistics rows to sum).
+ */
+int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_sumsq, const void* w_glob, int64_t N_glob, int64_t row0);
+int32_t cvmx_set_weight_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P);
+int32_t cvmx_slab_fold_sums(cvmx_t* h, int64_t f0, int64_t f1, void* carry);
+int32_t cvmx_slab_finalize_stats(cvmx_t* h, int64_t f0, int64_t f1, const void* raw);
 
 /* The validation rows of CSR fold `fold` for the caller's next step (predicting the held-out rows with a model built
  * from the training matrices - what ikpls does after training_XTX_XTY, cvmatrix/partitioner.py:27-31): out_X [n_val, K]

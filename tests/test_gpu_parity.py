@@ -527,9 +527,11 @@ def test_loo_both_forms_all_flag_combinations(dtype, K, M):
         scaled = flags[2] or flags[3]
 
         def ok(got, ref, truth, total, mode):
-            if f32 and mode == 0:
-                # the streaming form evaluates a float32 model in float64 and rounds once: it is closer to the float64
-                # evaluation than numpy-float32 is, and sits inside numpy-float32's own error band around it
+            if f32:
+                # numpy-float32 loses ~1e-5 of a centred leave-one-out matrix to cancellation (T - G in float32, sgemm
+                # totals), so 1e-5 AGAINST it is not a meaningful bar for any independent evaluation.  Held instead, for
+                # both forms: at least as close to the float64 evaluation of the same inputs as numpy-float32 is, and
+                # inside numpy-float32's own error band around it.
                 e_ref, e_us = rel_fro(ref, truth), rel_fro(got, truth)
                 return e_us <= 1.5 * e_ref + 1e-6 and rel_fro(got, ref) <= 2.5 * e_ref + 1e-5
             return _mat_ok(got, ref, total, tol, scaled)

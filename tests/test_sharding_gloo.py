@@ -89,3 +89,32 @@ def test_row_sharded_assembly_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_row_slab_csr_covers_every_fold_once():
+    """Row-slab mode: the local CSRs of all ranks, shifted back by their slab starts, reassemble every fold in order."""
+    import numpy as np
+
+    from cvmatrix_b200 import sharding
+
+    rng = np.random.default_rng(0)
+    N, P, world = 1003, 7, 3
+    labels = rng.integers(0, P, N)
+    order = np.argsort(labels, kind="stable")
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=P))]).astype(np.int64)
+    got = [[] for _ in range(P)]
+    covered = 0
+    for r in range(world):
+        r0, r1 = sharding.slab_rows(r, world, N)
+        covered += r1 - r0
+        loc_off, loc_idx = sharding.local_csr(offsets, order, r0, r1)
+        assert loc_idx.size == 0 or (loc_idx.min() >= 0 and loc_idx.max() < r1 - r0)
+        for f in range(P):
+            got[f].append(loc_idx[loc_off[f]:loc_off[f + 1]] + r0)
+    assert covered == N
+    for f in range(P):
+        assert np.array_equal(np.concatenate(got[f]), order[offsets[f]:offsets[f + 1]])
+    import pytest
+
+    with pytest.raises(ValueError, match="ascending"):
+        sharding.local_csr(np.array([0, 3]), np.array([5, 2, 9]), 0, 10)
