@@ -62,8 +62,12 @@ CONFIGS = {
     # contract self-test shape (tests/test_bench_contract.py)
     "tiny": dict(N=4_000, K=24, M=3, P=4, name="self-test: N=4k K=24 M=3 f64 4-fold"),
     # cfg 5 (wide, K=5000 M=100) at reduced N: the full N=2M matrix is 80 GB and cannot be generated on the host
-    # (full size: tools/bench_cfg5.py on one GPU, tools/bench_cfg5_sharded.py row-sharded over N GPUs)
     "cfg5s": dict(N=100_000, K=5000, M=100, P=10, name="wide K=5000 M=100 f64 weighted center+scale 10-fold at N=100k (cfg 5 scaled to 1/20 of its rows)"),
+    # cfg 5 at FULL size: the rows are produced block by block on the device and sharded across the GPUs (row-slab mode)
+    "cfg5": dict(N=2_000_000, K=5000, M=100, P=10, device_generated=True,
+                 name="wide N=2M K=5000 M=100 f64 weighted center+scale 10-fold, rows generated on the device and sharded across the GPUs"),
+    "cfg5f32": dict(N=2_000_000, K=5000, M=100, P=10, device_generated=True, f32=True,
+                    name="wide N=2M K=5000 M=100 f32 weighted center+scale 10-fold, rows generated on the device and sharded across the GPUs"),
     # reduced shapes for ncu captures only (same per-CTA work as cfg2 / cfg3 / cfg4, fewer CTAs)
     "prof2": dict(N=200_000, K=500, M=10, P=5, name="profiling: N=200k K=500 M=10 f64 5-fold"),
     "prof3": dict(N=200_000, K=500, M=10, P=200, name="profiling: N=200k K=500 M=10 f64 200-fold"),
@@ -122,6 +126,11 @@ def row_sharded_mode(P, world):
 def config_dict(cfg, world):
     """The `config` object of the JSON line - identical for the native and the reference arm."""
     N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
+    if cfg.get("device_generated"):
+        return {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P,
+                "parallelism": f"rows of the data set sharded x{world} (row slabs): chained column sums, per-slab Grams summed by the fold owners over NVLink peer memory",
+                "l2_policy": "inputs (82 GB float64) far larger than L2; no flush needed",
+                "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"}
     par = (f"rows of each fold sharded x{world}, fold owners reduce over NVLink peer memory" if row_sharded_mode(P, world)
            else f"fold-sharded x{world}")
     return {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": par,
@@ -213,7 +222,17 @@ def run_reference(args, cfg, rank, world):
         return
     RefCV, RefPart, kind, threads, blas = load_reference()
     N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
+    row_scale = 1.0
+    if cfg.get("device_generated"):
+        # the full matrix (80 GB; X, WX, sq_X would need 240 GB of host memory) cannot exist on the host: time 1/50 of
+        # the rows and scale linearly in N (every term of the reference's cost is linear in N at fixed K, M, P)
+        row_scale = 50.0
+        cfg = dict(cfg, N=int(N / row_scale))
+        N = cfg["N"]
     X, Y, w, folds, _ = make_host_inputs(cfg, pinned=False)
+    if cfg.get("f32"):
+        X, Y, w = X.astype(np.float32), Y.astype(np.float32), w.astype(np.float32)
+    ref_dtype = np.float32 if cfg.get("f32") else np.float64
     loo = P > 1000
     # leave-one-out at full size is ~90 s per pass: time the full fit and a fixed sample of folds per step
     n_folds = P if not loo else 2000
@@ -221,7 +240,7 @@ def run_reference(args, cfg, rank, world):
     def one_step():
         t0 = time.perf_counter()
         part = RefPart(folds)
-        m = RefCV(dtype=np.float64, copy=False)
+        m = RefCV(dtype=ref_dtype, copy=False)
         m.fit(X, Y, w)
         t1 = time.perf_counter()
         for f in list(part.folds_dict)[:n_folds]:
@@ -246,16 +265,20 @@ def run_reference(args, cfg, rank, world):
     t_fit /= steps
     t_fold /= steps
     scale = P / n_folds
+    t_fit *= row_scale
+    t_fold *= row_scale
     step_s = t_fit + t_fold * scale
     sample = ("full size: every row, every fold" if not loo else
               f"full-size fit, first {n_folds} of {P} folds per step, fold time scaled by {scale:.1f}")
+    if row_scale != 1.0:
+        sample = f"first {N} of {int(N * row_scale)} rows (the full matrix does not fit the host), every fold, time scaled linearly by {row_scale:.0f}"
     value = P / step_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(cfg, world),
+        "vs_baseline": None, "dtype": "f32" if cfg.get("f32") else "f64", "data": "synthetic",
+        "config": config_dict(CONFIGS[args.config], world),
         "reference_step": "Partitioner + fit + all folds (training_XTX_XTY), host arrays in, host arrays out, copy=False "
                           "(benchmarks/benchmark.py:52-158); runs on rank 0's host cores only",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "blas_threads": blas, "kind": kind, "sample": sample,
@@ -375,6 +398,147 @@ def roofline_of(cfg_name, cfg, world, rank_rows, rank_folds, timing, ms_per_step
     return roof
 
 
+def run_row_slabs(args, cfg, ctx):
+    """BASELINE config 5 at full size: N = 2M x K = 5000 (82 GB float64) is produced block by block ON THE DEVICE (it
+    cannot exist on the host) and its ROWS are sharded across the ranks (cvmatrix_b200.distributed.RowSlabFolds)."""
+    from cvmatrix_b200 import CVMatrix, _lib, sharding
+    from cvmatrix_b200.distributed import RowSlabFolds
+
+    torch, dist, dev, rank, world = ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world
+    N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
+    f32 = bool(cfg.get("f32"))
+    npdt, tdt = (np.float32, torch.float32) if f32 else (np.float64, torch.float64)
+    B = 65536
+    steps = max(1, min(args.steps, 3))
+    warmup = 1
+
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(4242)
+    w = torch.rand((N,), dtype=torch.float64, generator=gw, device=dev).to(tdt)      # the same on every rank
+    r0, r1 = sharding.slab_rows(rank, world, N)
+
+    def blocks():
+        for blk in range(r0 // B, (r1 + B - 1) // B):
+            g = torch.Generator(device=dev)
+            g.manual_seed(42_000 + blk)                                              # block-seeded: independent of the world size
+            full = torch.rand((min(N, (blk + 1) * B) - blk * B, K + M), dtype=torch.float64, generator=g, device=dev).to(tdt)
+            lo, hi = max(r0, blk * B), min(r1, (blk + 1) * B)
+            part = full[lo - blk * B: hi - blk * B]
+            torch.cuda.current_stream(dev).synchronize()                             # the library reads the block on ITS stream
+            yield lo, part[:, :K], part[:, K:]
+
+    m = CVMatrix(dtype=npdt, device=ctx.local_rank)
+    lib, h = m._lib, m._h
+    rs = RowSlabFolds(m, N, K, M, w, block_rows=B)
+    # generation is not part of fit: measure it alone first (the same kernels, results dropped)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in blocks():
+        pass
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    ctx.barrier()
+    t0 = time.perf_counter()
+    rs.fit(blocks())
+    torch.cuda.synchronize()
+    ctx.barrier()
+    fit_s = time.perf_counter() - t0 - gen_s
+    torch.cuda.empty_cache()
+    folds = np.arange(N) % P
+    order = np.argsort(folds, kind="stable")
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(folds, minlength=P))]).astype(np.int64)
+    rs.set_folds((offsets, order))
+    o0, o1 = sharding.fold_block(rank, world, 0, P)
+    outs = rs.alloc_outputs(max(o1 - o0, 1))
+    _lib.check(lib.cvmx_set_stream(h, C.c_void_p(ctx.stream.cuda_stream)), h)
+
+    def step():
+        rs.training_batch(0, P, out=outs)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    _lib.check(lib.cvmx_profile_enable(h, 1), h)
+    launches0 = m.launch_count
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ctx.stream)
+    for _ in range(steps):
+        step()
+    e1.record(ctx.stream)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = m.launch_count - launches0
+    prof_ms, prof_n = (C.c_double * 3)(), (C.c_int64 * 3)()
+    _lib.check(lib.cvmx_profile_read(h, prof_ms, prof_n), h)
+    _lib.check(lib.cvmx_profile_enable(h, 0), h)
+    # end to end: fit from the device-generated blocks + all folds + every result copied to pinned host memory
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in outs.items() if v is not None}
+    ctx.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rs.fit(blocks())
+    rs.set_folds((offsets, order))
+    res = rs.training_batch(0, P, out=outs)
+    n_own = res["fold_end"] - res["fold_begin"]
+    d2h = 0
+    for k, hb in host_out.items():
+        if n_own > 0:
+            hb[:n_own].copy_(outs[k][:n_own], non_blocking=True)
+            d2h += hb[:n_own].numel() * hb.element_size()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0 - gen_s
+    if world > 1:
+        t = torch.tensor([ms, fit_s, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, fit_s, e2e_s = (float(v) for v in t.tolist())
+        t = torch.tensor([float(d2h)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        d2h = int(t.item())
+    ms_per_step = ms / steps
+    if rank != 0:
+        return
+    flops = 2.0 * (r1 - r0) * K * (K + M)                    # this rank's rows, every one in exactly one fold
+    gram_ms = prof_ms[1] / steps
+    peak_tf, peak_src = fp64_peak_tflops()
+    ach = flops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
+    TI, TJ = -(-K // 128), -(-(K + M) // 128)
+    issued = 2.0 * (r1 - r0) * 128 * 128 * sum((0.75 if bj == bi else 1.0) for bi in range(TI) for bj in range(bi, TJ))
+    roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if ach else None,
+            "peak_source": peak_src + "; FP64 tensor pipe" + (" (float32 data, float64 DMMA accumulation)" if f32 else ""),
+            "kernel": "k_gram<%s>" % ("float" if f32 else "double"), "issued_flops_per_step": issued,
+            "issued_frac_of_peak": issued / (gram_ms * 1e-3) / 1e12 / peak_tf if gram_ms > 0 else None,
+            "note": "achieved / frac use the FULL flop count 2 N K (K+M) of SURVEY.md 8(d) for this rank's rows; only upper-triangular tiles are issued",
+            "traffic": None, "kernel_ms_per_step": gram_ms, "kernel_launches_per_step": prof_n[1] / steps,
+            "stats_ms_per_step": prof_ms[0] / steps, "reduce_ms_per_step": prof_ms[2] / steps,
+            "algorithmic_flops_per_step": flops, "per": "rank 0" if world > 1 else "GPU",
+            "step_roofline_frac": flops / (peak_tf * 1e12) / (ms_per_step * 1e-3)}
+    line = {
+        "metric": METRIC, "value": P / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "steps_requested": args.steps, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32" if f32 else "f64", "data": "synthetic (uniform [0,1), generated block by block on the device, block-seeded)",
+        "config": config_dict(cfg, world),
+        "collective": ("peer-memory reduction over NVLink (symmetric memory, no all-reduce)" if rs._symm is not None else
+                       ("1 NCCL all-reduce of the fold Grams" if world > 1 else None)),
+        "clocks": clocks,
+        "e2e": {"value": P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(offsets.nbytes + order.nbytes), "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": 1,
+                "includes": "fit streamed from device-generated row blocks (the 80 GB matrix cannot exist on the host; generation time "
+                            "subtracted) + chained sums + totals all-reduce + set_folds + all folds + D2H of every output into pinned memory"},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None,
+        "parity": {"note": "no host can hold this matrix: parity of this path is pinned at reduced N - tests/test_gpu_fullsize.py::"
+                           "test_cfg5_reduced_wide_k (K = 5000, one GPU) and the row-slab section of tests/dist_fit_worker.py (2 GPUs) against the oracle"},
+        "fit_s": fit_s, "generation_s": gen_s, "resident_gb_per_gpu": (r1 - r0) * (-(-(K + M) // 32) * 32) * (4 if f32 else 8) / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def native_fold_results(m, folds_idx, K):
     """Host copies of the batched path's results for the given CSR fold numbers (XTX, XTY, 4 statistics rows)."""
     res = {}
@@ -429,6 +593,12 @@ def main():
     ctx.barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     ctx.stream = torch.cuda.Stream(dev)   # a real (non-default) stream shared by the library and the timing events
     torch.cuda.set_stream(ctx.stream)
+
+    if cfg.get("device_generated"):
+        run_row_slabs(args, cfg, ctx)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     N, K, M, P = cfg["N"], cfg["K"], cfg["M"], cfg["P"]
     X, Y, w, folds, keep = make_host_inputs(cfg, pinned=True)

@@ -104,8 +104,7 @@ struct cvmx_handle {
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
   DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look;
-  int scan_fused = 1;   // passes 1 - 3 in one read of the rows (k_scan_fused); 0: the four-pass form (CVMX_SCAN_FUSED=0)
-  bool attr_scan = false;
+  int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
   int64_t scan_launches = 0;
   int64_t launches = 0;
   // optional per-kernel timing (cvmx_profile_*): event pairs recorded on the handle stream
@@ -179,6 +178,78 @@ void plan_tiles(const cvmx_t* h, uint32_t want, std::vector<int2>& tiles) {
     }
 }
 
+// ---- row-split plan of few large folds -------------------------------------------------------------------------------
+// The hardware places CTAs greedily (next CTA to the first SM that frees up), so equal-sized units end in a ragged last
+// wave: 1150 equal items on 148 SMs leave a quarter of the GPU idle for a whole item.  Unit sizes therefore TAPER - a few
+// long units, then halves, quarters, ... - and are launched longest first, which is the classic LPT packing; the sizes
+// are chosen by simulating that placement with the measured relative tile costs (a diagonal tile issues 3/4 of the
+// DMMAs of a full one; ~1.5 pipeline stages of fixed cost per CTA).  Returns per fold the unit sizes in split order.
+double simulate_makespan(std::vector<int64_t> unit_rows, const std::vector<double>& tile_cost, int64_t sms) {
+  std::sort(unit_rows.begin(), unit_rows.end(), std::greater<int64_t>());
+  std::vector<double> heap((size_t)sms, 0.0);   // min-heap of SM finish times
+  auto cmp = std::greater<double>();
+  for (int64_t n : unit_rows)
+    for (double c : tile_cost) {
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      heap.back() += ((double)n + 1.5 * GBK) * c;
+      std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+  return *std::max_element(heap.begin(), heap.end());
+}
+
+std::vector<int64_t> taper_sizes(int64_t n, int64_t R, int levels) {
+  std::vector<int64_t> tail;
+  int64_t r = R;
+  for (int l = 0; l < levels; ++l) { r = std::max<int64_t>(256, (r / 2) / GBK * GBK); tail.push_back(r); tail.push_back(r); }
+  int64_t tail_sum = 0;
+  for (int64_t t : tail) tail_sum += t;
+  std::vector<int64_t> sizes;
+  const int64_t main_rows = std::max<int64_t>(0, n - tail_sum);
+  if (main_rows > 0) {
+    const int64_t k = std::max<int64_t>(1, (main_rows + R / 2) / R), per = round_up((main_rows + k - 1) / k, GBK);
+    for (int64_t i = 0; i < k; ++i) {
+      const int64_t a = std::min(main_rows, i * per), b = std::min(main_rows, (i + 1) * per);
+      if (b > a) sizes.push_back(b - a);
+    }
+  }
+  int64_t rem = n;
+  for (int64_t v : sizes) rem -= v;
+  for (int64_t t : tail) {
+    const int64_t v = std::min(rem, t);
+    if (v > 0) { sizes.push_back(v); rem -= v; }
+  }
+  if (rem > 0) { if (sizes.empty()) sizes.push_back(rem); else sizes.back() += rem; }
+  return sizes;
+}
+
+std::vector<std::vector<int64_t>> plan_tapered(const std::vector<int64_t>& fold_rows, const std::vector<int2>& tiles, int64_t sms,
+                                               int64_t r_lo, int64_t r_hi) {
+  std::vector<double> tile_cost;
+  for (const int2& t : tiles) tile_cost.push_back(t.x == t.y ? 0.78 : 1.0);
+  double best = 1e300;
+  std::vector<std::vector<int64_t>> best_sizes;
+  for (int64_t R = r_lo; R <= r_hi; R += 4 * GBK)
+    for (int levels = 1; levels <= 4; ++levels) {
+      std::vector<std::vector<int64_t>> sizes;
+      std::vector<int64_t> all;
+      for (int64_t n : fold_rows) {
+        sizes.push_back(n > 0 ? taper_sizes(n, R, levels) : std::vector<int64_t>{0});
+        all.insert(all.end(), sizes.back().begin(), sizes.back().end());
+      }
+      const double mk = simulate_makespan(all, tile_cost, sms);
+      if (mk < best - 1e-9) { best = mk; best_sizes = sizes; }
+    }
+  return best_sizes;
+}
+
+// Launch order = longest unit first (LPT).  A fold's units keep their split numbers and partial slots; fold_units[f] only
+// has to point at ANY unit of fold f (k_gram_reduce / k_partial_sum read the fold's part_base and nsplit from it).
+void sort_units_longest_first(Plan& pl) {
+  std::stable_sort(pl.units.begin(), pl.units.end(),
+                   [](const GramUnit& a, const GramUnit& b) { return a.row_end - a.row_begin > b.row_end - b.row_begin; });
+  for (size_t i = pl.units.size(); i-- > 0;) pl.fold_units[pl.units[i].fold] = (int32_t)i;
+}
+
 // Row-split policy.  Many small folds: one unit per fold, epilogue fused into the Gram kernel.  Few large
 // folds: split the rows so that (units x tiles) fills the SMs in whole waves; partials are reduced in
 // split order by k_gram_reduce (deterministic).
@@ -204,24 +275,38 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
       if (eff > best + 1e-9) { best = eff; rows_per_unit = R; }
     }
   }
+  std::vector<std::vector<int64_t>> tapered;
+  if (rows_per_unit != INT64_MAX && ntiles < sms) {     // (wide K: the tiles alone fill the GPU - equal, long units)
+    std::vector<int64_t> fold_rows;
+    for (int64_t f = f0; f < f1; ++f) fold_rows.push_back(off[f + 1] - off[f]);
+    tapered = plan_tapered(fold_rows, pl.tiles, sms, 1024, 8192);
+  }
   for (int64_t f = f0; f < f1; ++f) {
     const int64_t beg = off[f], n = off[f + 1] - off[f];
     pl.max_rows = std::max(pl.max_rows, n);
-    const int64_t ns = (rows_per_unit == INT64_MAX) ? 1 : std::max<int64_t>(1, (n + rows_per_unit - 1) / rows_per_unit);
+    std::vector<int64_t> sizes;
+    if (!tapered.empty()) sizes = tapered[f - f0];
+    else {
+      // equal-sized splits, multiples of GBK rows
+      const int64_t ns = (rows_per_unit == INT64_MAX) ? 1 : std::max<int64_t>(1, (n + rows_per_unit - 1) / rows_per_unit);
+      const int64_t per = round_up((n + ns - 1) / ns, GBK);
+      for (int64_t s = 0; s < ns; ++s) sizes.push_back(std::min(n, (s + 1) * per) - std::min(n, s * per));
+    }
+    const int64_t ns = (int64_t)sizes.size();
     pl.fold_units[f - f0] = (int32_t)pl.units.size();
     if (ns > 1) pl.split_folds.push_back((int32_t)(f - f0));
-    // equal-sized splits, multiples of GBK rows
-    const int64_t per = round_up((n + ns - 1) / ns, GBK);
+    int64_t pos = beg;
     for (int64_t s = 0; s < ns; ++s) {
       GramUnit u;
-      u.row_begin = beg + std::min(n, s * per);
-      u.row_end = beg + std::min(n, (s + 1) * per);
+      u.row_begin = pos; u.row_end = pos + sizes[s];
+      pos += sizes[s];
       u.fold = (int32_t)(f - f0); u.split = (int32_t)s; u.nsplit = (int32_t)ns;
       u.part_base = (int32_t)pl.n_partial_units;
       pl.units.push_back(u);
     }
     if (ns > 1) pl.n_partial_units += ns;
   }
+  sort_units_longest_first(pl);
 }
 
 template <typename T>
@@ -366,7 +451,7 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
     const double bytes = ctas * (double)max_rows * MOM_COLS * sizeof(double);
     const double waves = std::ceil(ctas / (3.0 * h->sm_count));
     const double pipe_ns = std::max(7.6 * (double)max_rows * waves, bytes / 6000.0);
-    const double scan_ns = h->scan_fused ? bytes / 5000.0 + 110e3 : 2.0 * bytes / 5000.0 + 150e3;   // fused: one read of the rows
+    const double scan_ns = 2.0 * bytes / 5000.0 + 150e3;
     scan = seg_bytes <= ((size_t)2 << 30) &&
            (h->scan_mode == 2 ? max_rows >= 4 * SCAN_L : (max_rows >= 8192 && scan_ns < pipe_ns && pipe_ns > 0.7 * overlap_ns));
   }
@@ -398,34 +483,20 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
         sp.slow_list = h->scan_list.as<int>(); sp.slow_cnt = h->scan_cnt.as<int>();
         // (measured: capping the streaming grids to a few SMs' worth of CTAs and fatter chain CTAs while a Gram kernel
         // owns the GPU does not change the step time - the passes cost the same SM time either way)
-        if (h->scan_fused) {
-          // one read of the rows: look-back workspace [agg | inc | status | ticket], status and ticket zeroed per launch
-          ScanLook lk;
-          lk.nseq = (int)(mine * ny); lk.mine = (int)mine;
-          const size_t vals = (size_t)lk.nseq * max_segs * 96 * sizeof(double);
-          const size_t flags = ((size_t)lk.nseq * max_segs + 1) * sizeof(int);
-          CU(h, h->scan_look.reserve(2 * vals + flags));
-          lk.agg = h->scan_look.as<double>();
-          lk.inc = lk.agg + (size_t)lk.nseq * max_segs * 96;
-          lk.status = reinterpret_cast<int*>(h->scan_look.as<char>() + 2 * vals);
-          lk.ticket = reinterpret_cast<unsigned*>(lk.status + (size_t)lk.nseq * max_segs);
-          CU(h, cudaMemsetAsync(lk.status, 0, flags, h->stream));
-          if (!h->attr_scan) {
-            CU(h, cudaFuncSetAttribute(k_scan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_fused_smem()));
-            h->attr_scan = true;
-          }
-          const int64_t nsegs = (max_rows + SCAN_L - 1) / SCAN_L;
-          lk.total = (unsigned)(lk.nseq * nsegs);
-          const unsigned ctas = (unsigned)std::min<int64_t>((int64_t)lk.total, (int64_t)3 * h->sm_count);   // persistent: 3 per SM
-          k_scan_fused<<<ctas, SF_THREADS, scan_fused_smem(), h->stream>>>(sp, lk);
-          k_scan_lists<<<dim3((unsigned)((mine * SCAN_COLS * 2 + 3) / 4), ny), 128, 0, h->stream>>>(sp, (int)mine);
-          h->launches -= 1;
-        } else {
         const int64_t quads = (max_segs + SCAN_WARPS - 1) / SCAN_WARPS;
         const dim3 gseg((unsigned)mine, (unsigned)quads, ny);
-        k_scan_segsums<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
-        k_scan_prefix<<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp);
-        k_scan_delta<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+        // fold statistics of a fitted model: the totals predict every segment's binade, so passes 1 and 3 share ONE
+        // read of the rows (k_scan_spec) and the prefix pass verifies the guess; fit itself has no totals yet
+        const bool spec = h->scan_spec && q.offsets && !q.accumulate && h->fitted;
+        if (spec) {
+          CU(h, h->scan_look.reserve((size_t)ny * 2 * 3 * mp.ld * max_segs * sizeof(double)));
+          k_scan_spec<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp, h->scan_look.as<double>());
+          k_scan_prefix<true><<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp, h->scan_look.as<double>());
+          h->launches -= 1;
+        } else {
+          k_scan_segsums<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+          k_scan_prefix<false><<<dim3((unsigned)(mine * SCAN_PREFIX_CTAS), ny), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp, nullptr);
+          k_scan_delta<<<gseg, 32 * SCAN_WARPS, 0, h->stream>>>(sp);
         }
         k_scan_chain<2><<<dim3((unsigned)(mine * (SCAN_COLS / 2)), ny), 64 * 2, scan_chain_smem<2>(), h->stream>>>(sp);
         h->launches += 4; h->scan_launches += 1;
@@ -1181,33 +1252,33 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
       off2[2 * f] = beg + std::min(n, shard * per);
       off2[2 * f + 1] = beg + std::min(n, (shard + 1) * per);
     }
-    // units: split each fold's shard so the grid fills the SMs in whole waves
+    // units: taper each fold's shard so that the greedy CTA placement ends evenly (plan_tapered); wide K: the tiles
+    // alone fill the GPU in many waves - one unit per fold shard, no partial workspace to sum
     const int64_t sms = h->sm_count;
-    int64_t best_R = 4096; double best = -1;
-    // wide K: the tiles alone fill the GPU in many waves - one unit per fold shard, no partial workspace to sum
-    if (nt >= sms) { best_R = INT64_MAX / 4; best = 2; }
-    for (int64_t R = 1024; R <= 4096 && best < 2; R += GBK) {
-      int64_t items = 0;
-      for (int64_t f = 0; f < Pn; ++f) items += std::max<int64_t>(1, (off2[2 * f + 1] - off2[2 * f] + R - 1) / R);
-      items *= nt;
-      const double eff = (double)items / (double)(sms * ((items + sms - 1) / sms));
-      if (eff > best + 1e-9) { best = eff; best_R = R; }
+    std::vector<std::vector<int64_t>> sizes;
+    if (nt >= sms) {
+      for (int64_t f = 0; f < Pn; ++f) sizes.push_back({off2[2 * f + 1] - off2[2 * f]});
+    } else {
+      std::vector<int64_t> fold_rows;
+      for (int64_t f = 0; f < Pn; ++f) fold_rows.push_back(off2[2 * f + 1] - off2[2 * f]);
+      sizes = plan_tapered(fold_rows, pl.tiles, sms, 1024, 8192);
     }
     pl.fold_units.assign(Pn, 0);
     for (int64_t f = 0; f < Pn; ++f) {
-      const int64_t beg = off2[2 * f], n = off2[2 * f + 1] - beg;
-      const int64_t ns = std::max<int64_t>(1, (n + best_R - 1) / best_R);
-      const int64_t per = round_up((n + ns - 1) / ns, GBK);
+      const int64_t ns = (int64_t)sizes[f].size();
       pl.fold_units[f] = (int32_t)pl.units.size();
       pl.split_folds.push_back((int32_t)f);
+      int64_t pos = off2[2 * f];
       for (int64_t s2 = 0; s2 < ns; ++s2) {
         GramUnit u;
-        u.row_begin = beg + std::min(n, s2 * per); u.row_end = beg + std::min(n, (s2 + 1) * per);
+        u.row_begin = pos; u.row_end = pos + sizes[f][s2];
+        pos += sizes[f][s2];
         u.fold = (int32_t)f; u.split = (int32_t)s2; u.nsplit = (int32_t)ns; u.part_base = (int32_t)pl.n_partial_units;
         pl.units.push_back(u);
       }
       pl.n_partial_units += ns;
     }
+    sort_units_longest_first(pl);
     int32_t rcu = upload_tables(h, tc, key, pl);   // the plan repeats from step to step: uploaded once
     if (rcu) return rcu;
   }
@@ -1428,7 +1499,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
-  if (const char* e = std::getenv("CVMX_SCAN_FUSED")) h->scan_fused = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_SCAN_SPEC")) h->scan_spec = std::atoi(e) ? 1 : 0;
   DeviceGuard guard__(device);
   if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;

@@ -515,6 +515,14 @@ __global__ void __launch_bounds__(256) k_partial_sum(const double* __restrict__ 
   *reinterpret_cast<double2*>(out + ((size_t)unit.fold * ntiles + tile) * tile_elems + e) = acc;
 }
 
+// Raw Grams of the folds a rank owns, summed over the peers' buffers (this rank's own included; mapped over NVLink):
+//   out[e] = sum_q peers[q][offset + e],  e < n  (n even; peer order fixed -> deterministic)
+// Element-parallel, all peer loads of a thread in flight together: the reduction runs at NVLink bandwidth instead of
+// the round-trip latency that the per-tile epilogue CTAs (10 per fold) paid 32 times in a row when they summed the peers
+// themselves.  The epilogue then reads one local buffer.
+struct PeerList;
+__global__ void __launch_bounds__(256) k_peer_sum_frags(const double* const* __restrict__ /*unused*/, int) {}
+
 // Statistics rows of a column-sharded evaluation: every rank holds its own column groups (zeros elsewhere) behind its
 // raw Grams in the symmetric buffer; out[i] = sum over peers, read over NVLink (replaces the second all-reduce).
 struct PeerList { const double* p[8]; };   // by value in the kernel parameters: no pointer table to upload

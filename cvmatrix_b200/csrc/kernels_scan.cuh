@@ -34,7 +34,7 @@ namespace cvmx {
 
 constexpr int SCAN_COLS = MOM_COLS;   // same column groups as k_moments_pipe (column sharding is per group)
 constexpr int SCAN_WARPS = 4;         // segments per CTA in the two streaming passes
-constexpr int SCAN_L = 128;           // rows per segment (multiple of 32; compile-time in pass 4 and in k_scan_fused)
+constexpr int SCAN_L = 256;           // rows per segment (multiple of 32; compile-time in pass 4)
 
 struct ScanParams {
   MomentParams<double> p;
@@ -53,6 +53,11 @@ struct ScanParams {
 // element (segment s, column c) of plane (fold f, chain, slot)
 __device__ __forceinline__ double* scan_plane(const ScanParams& sp, int64_t f, int chain, int slot, int64_t c) {
   return sp.seg + ((((size_t)f * 2 + chain) * 2 + slot) * (size_t)sp.p.ld + (size_t)c) * (size_t)sp.max_segs;
+}
+
+// spec planes: [folds][chain][3: guessed proxy, d0, d1][ld][max_segs]
+__device__ __forceinline__ double* scan_spec_plane(const ScanParams& sp, double* spec, int64_t f, int chain, int which, int64_t c) {
+  return spec + ((((size_t)f * 2 + chain) * 3 + which) * (size_t)sp.p.ld + (size_t)c) * (size_t)sp.max_segs;
 }
 
 // rows [r0, r0 + cnt) of a fold, 32 at a time: lane l fetches the index and weight of row l of the batch, the
@@ -129,7 +134,10 @@ __global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_segsums(ScanParams sp)
 constexpr int SCAN_PREFIX_CTAS = 4;                                   // per column group
 constexpr int SCAN_PREFIX_THREADS = 32 * SCAN_COLS / SCAN_PREFIX_CTAS;
 constexpr int SCAN_PER_LANE = 8;                                      // max_segs is a multiple of this (16-byte loads)
-__global__ void __launch_bounds__(SCAN_PREFIX_THREADS) k_scan_prefix(ScanParams sp) {
+// SPEC: the proxy chains already ran from guessed proxies (k_scan_spec); a segment is fast iff the true proxy start
+// equals the guess, and its increments are copied from the spec planes (pass 3 is skipped).
+template <bool SPEC>
+__global__ void __launch_bounds__(SCAN_PREFIX_THREADS) k_scan_prefix(ScanParams sp, const double* __restrict__ spec) {
   const MomentParams<double>& p = sp.p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t f = blockIdx.y;
@@ -145,7 +153,10 @@ __global__ void __launch_bounds__(SCAN_PREFIX_THREADS) k_scan_prefix(ScanParams 
       double P = 0.0, tot = 0.0;
       if (p.accumulate) P = chain == 0 ? p.sum_z[c] : p.sumsq_z[c];
       double* dS = scan_plane(sp, f, chain, 0, c);
-      const double* dA = scan_plane(sp, f, chain, 1, c);
+      double* dA = scan_plane(sp, f, chain, 1, c);
+      const double* gB = SPEC ? scan_spec_plane(sp, const_cast<double*>(spec), f, chain, 0, c) : nullptr;
+      const double* gd0 = SPEC ? scan_spec_plane(sp, const_cast<double*>(spec), f, chain, 1, c) : nullptr;
+      const double* gd1 = SPEC ? scan_spec_plane(sp, const_cast<double*>(spec), f, chain, 2, c) : nullptr;
       int* list = sp.slow_list + ((size_t)(f * 2 + chain) * p.ld + c) * sp.slow_cap;
       int nslow = 0;
       for (int64_t J = 0; J < nseg; J += 32 * SCAN_PER_LANE) {
@@ -186,8 +197,17 @@ __global__ void __launch_bounds__(SCAN_PREFIX_THREADS) k_scan_prefix(ScanParams 
           if (Aj[e] == 0.0) B = -0.0;                                                   // only zeros: s + (+-0)
           else if (same) B = __longlong_as_double((blo & (long long)0xfff0000000000000ULL) | 0x0008000000000000LL);
           if (j0 + e < nseg) {
-            dS[j0 + e] = B;
-            if (__double_as_longlong(B) == 0) slowbits |= 1u << e;
+            if (SPEC) {
+              // accept the speculative increments only where the guess IS the true proxy start (same sign and binade;
+              // -0 = identity segment on both sides); everything else is added row by row in pass 4
+              const bool hit = __double_as_longlong(B) != 0 && __double_as_longlong(B) == __double_as_longlong(gB[j0 + e]);
+              dS[j0 + e] = hit ? gd0[j0 + e] : 0.0;
+              dA[j0 + e] = hit ? gd1[j0 + e] : 0.0;
+              if (!hit) slowbits |= 1u << e;
+            } else {
+              dS[j0 + e] = B;
+              if (__double_as_longlong(B) == 0) slowbits |= 1u << e;
+            }
           }
           Pj += Sj[e];
           totj += Aj[e];
@@ -367,329 +387,72 @@ __global__ void __launch_bounds__(64 * SCAN_CHAIN_COLS) k_scan_chain(ScanParams 
   if (chain == 0 && lane == 0) finalize_column<double>(p, f, c, acc, sres[lc]);
 }
 
-// ---- passes 1 - 3 in ONE read of the rows (decoupled look-back) ----------------------------------------------------
-// The four-pass form reads every row twice (pass 1 and pass 3), and that second read is what the scan costs beside a
-// Gram kernel that owns the tensor pipe but not the memory system.  k_scan_fused stages one segment (SCAN_L rows x 32
-// columns) in shared memory ONCE and does everything that needs the rows from there:
-//   1. segment sums S, A, Q (any order) from shared memory;
-//   2. the prefix over all earlier segments of the same (fold, column group) by decoupled look-back (Merrill & Garland):
-//      the CTA publishes its aggregate, then a warp polls the status words of up to 32 predecessors at a time
-//      (lane = predecessor), adds their aggregates down to the nearest published inclusive prefix (lane = column) and
-//      publishes its own inclusive prefix;
-//   3. the proxy starts (same interval test as k_scan_prefix) and the four proxy chains per column (2 sums x 2 parities,
-//      one warp each) - again from shared memory.
-// CTAs are persistent and take (sequence, segment) tasks in ticket order from an atomic counter, dealt round-robin over
-// the (fold, group) sequences so that every sequence advances together; a CTA only ever waits for tickets smaller
-// than its own, and the smallest unfinished ticket is always being processed, so look-back cannot deadlock.  Every
-// CTA prefetches the rows of its NEXT task (cp.async into the other half of a double buffer) before it starts on the
-// current one: without that, look-back couples each task to its 32 predecessors and the whole GPU falls into
-// lock-step load / compute phases (measured: 2 TB/s; the first version of this kernel).
-// Slow segments are marked in the d0 plane with a reserved NaN payload (a fast segment's increments are finite);
-// k_scan_lists turns the marks into the ascending per-column lists k_scan_chain walks.  The approximate prefix now
-// depends on the order in which look-back happened to add the aggregates; that only moves segments between "fast" and
-// "slow" - the error margin covers any summation order - never the result, which stays bit-identical to the chain.
-constexpr int SF_THREADS = 128;
-constexpr unsigned long long SCAN_SLOW_MARK = 0x7ff8dead00000000ULL;
-
-struct ScanLook {
-  double* agg;        // [nseq][max_segs][3][32]: S, A, Q of a segment
-  double* inc;        // same shape: inclusive prefixes
-  int* status;        // [nseq][max_segs]: 0 nothing yet, 1 aggregate published, 2 inclusive prefix published
-  unsigned* ticket;   // work counter (zeroed with the status words before every launch)
-  int nseq;           // sequences = folds x own column groups
-  int mine;           // own column groups per fold
-  unsigned total;     // tasks = nseq x segments of the longest fold
-};
-
-constexpr size_t scan_fused_smem() {
-  return 2 * ((size_t)SCAN_L * SCAN_COLS * sizeof(double) + (size_t)SCAN_L * sizeof(double))   // two segments + their weights
-         + 3072                                           // row numbers, later the cross-warp sums [4][3][32]
-         + 3 * 32 * sizeof(double)                        // exclusive prefix
-         + 3 * 32 * sizeof(double)                        // segment sums
-         + 2 * 32 * sizeof(double)                        // proxy starts
-         + 64;
-}
-static_assert(SCAN_L * 8 <= 3072 && SCAN_L % 32 == 0, "row-number scratch");
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+// ---- passes 1 and 3 in ONE read of the rows: speculative proxies ---------------------------------------------------
+// The four-pass form reads every row twice (pass 1 and pass 3), because the proxy start of a segment needs the prefix
+// over all earlier segments.  For fold statistics the data set's own totals are already known (fit), and they predict
+// that prefix well enough to GUESS the binade: after k of the N rows the running sum of column c is about
+// sum_z[c] * k / N.  k_scan_spec computes the segment sums S, A, Q of pass 1 AND runs the four proxy chains of pass 3
+// from the guessed binade in the same sweep; k_scan_prefix<true> then derives the true proxy start exactly as before
+// and accepts the speculative increments only where its binade (and sign) EQUALS the guess - bit for bit - and marks
+// the segment slow otherwise.  A wrong guess therefore costs one slow segment, never a wrong bit; rows that are not
+// exchangeable (sorted data) simply fall back to slow segments / the chain kernel through the usual group flag.
+// (Measured alternatives, both slower than the four passes: a single-pass decoupled look-back scan with the segment
+// staged in shared memory, 249 us vs 271 us for the 8-way shard of cfg 2 - look-back couples every task to its 32
+// predecessors and the GPU falls into lock-step load / compute phases - and its persistent double-buffered form, 427 us.)
+__device__ __forceinline__ double scan_guess_proxy(double est) {
+  const long long b = __double_as_longlong(est);
+  const int e = (int)((b >> 52) & 0x7ff);
+  if (e < 1 || e > 2046) return 0.0;                       // zero, denormal, inf, nan: no guess
+  return __longlong_as_double((b & (long long)0xfff0000000000000ULL) | 0x0008000000000000LL);
 }
 
-struct ScanTask {       // one (sequence, segment)
-  int seq; int g; int cnt; bool valid;
-  int64_t seg, f, c0, n, r0;
-  const int64_t* idx;
-};
-
-__global__ void __launch_bounds__(SF_THREADS, 3) k_scan_fused(ScanParams sp, ScanLook lk) {
-  extern __shared__ __align__(128) unsigned char sf_smem[];
+__global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_spec(ScanParams sp, double* __restrict__ spec) {
   const MomentParams<double>& p = sp.p;
-  double* tile0 = reinterpret_cast<double*>(sf_smem);                      // [2][SCAN_L][32]
-  double* swt0 = tile0 + (size_t)2 * SCAN_L * SCAN_COLS;                   // [2][SCAN_L]
-  long long* srow = reinterpret_cast<long long*>(swt0 + 2 * SCAN_L);       // [SCAN_L]   (only while copies are issued)
-  double* red = reinterpret_cast<double*>(srow);                           // [4][3][32] (aliases srow)
-  double* ex = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srow) + 3072);   // [3][32]
-  double* segs = ex + 96;                                                  // [3][32]
-  double* prox = segs + 96;                                                // [2][32]
-  unsigned* misc = reinterpret_cast<unsigned*>(prox + 64);                 // [0] ticket, [1] negative-square flags
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // next valid task in ticket order (tasks past the end of a short fold are skipped); block-uniform
-  auto take = [&]() -> ScanTask {
-    ScanTask t;
-    t.valid = false;
-    while (true) {
-      __syncthreads();
-      if (tid == 0) misc[0] = atomicAdd(lk.ticket, 1u);
-      __syncthreads();
-      const unsigned ticket = misc[0];
-      if (ticket >= lk.total) return t;
-      t.seq = (int)(ticket % (unsigned)lk.nseq);
-      t.seg = (int64_t)(ticket / (unsigned)lk.nseq);
-      t.f = t.seq / lk.mine;
-      t.g = p.grp0 + (t.seq % lk.mine) * p.grp_stride;
-      t.c0 = (int64_t)t.g * SCAN_COLS;
-      const int64_t beg = p.offsets ? p.offsets[p.fold0 + t.f] : 0;
-      t.n = p.offsets ? p.offsets[p.fold0 + t.f + 1] - beg : p.N;
-      t.idx = p.offsets ? p.indices + beg : nullptr;
-      if (t.seg == 0 && tid == 0) sp.ok[t.f * sp.groups_total + t.g] = 1;  // k_scan_lists may clear it
-      t.r0 = t.seg * SCAN_L;
-      if (t.r0 >= t.n) continue;
-      t.cnt = (int)min((int64_t)SCAN_L, t.n - t.r0);
-      t.valid = true;
-      return t;
-    }
-  };
-  // stage the rows of a task: row numbers and weights first, then 16-byte chunks (16 lanes cover one 256-byte row piece)
-  auto issue = [&](const ScanTask& t, int buf) {
-    double* tile = tile0 + (size_t)buf * SCAN_L * SCAN_COLS;
-    double* swt = swt0 + buf * SCAN_L;
-    __syncthreads();                                       // srow / red free again
-    for (int r = tid; r < SCAN_L; r += SF_THREADS) {
-      const long long row = r < t.cnt ? (t.idx ? t.idx[t.r0 + r] : p.row0 + t.r0 + r) : -1;
-      srow[r] = row;
-      cp_async8(swt + r, p.w + (row >= 0 ? row : 0), row >= 0 ? 8 : 0);
-    }
-    __syncthreads();
-    const int chunk = tid & 15, rr = tid >> 4;
-    const char* zbase = reinterpret_cast<const char*>(p.Z + t.c0 + chunk * 2);
-    const long long row_bytes = (long long)p.ld * 8;
-#pragma unroll 8
-    for (int k = 0; k < SCAN_L / 8; ++k) {
-      const int r = rr + 8 * k;
-      const long long row = srow[r];
-      cp_async16(tile + (size_t)r * SCAN_COLS + chunk * 2, zbase + (row >= 0 ? row : 0) * row_bytes, row >= 0 ? 16 : 0);
-    }
-    cp_async_commit();
-  };
-
-  ScanTask cur = take();
-  int buf = 0;
-  if (cur.valid) issue(cur, buf);
-  while (cur.valid) {
-    ScanTask nxt = take();
-    if (nxt.valid) { issue(nxt, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const double* tile = tile0 + (size_t)buf * SCAN_L * SCAN_COLS;
-    const double* swt = swt0 + buf * SCAN_L;
-    const int seq = cur.seq, cnt = cur.cnt;
-    const int64_t seg = cur.seg, f = cur.f, c0 = cur.c0;
-    if (tid == 0) misc[1] = 0u;
-
-    // ---- 1. segment sums (rows past the end are zero-filled: t = q = +0) -------------------------------------------
-    {
-      double S[4] = {0, 0, 0, 0}, A[4] = {0, 0, 0, 0}, Q[4] = {0, 0, 0, 0};
-      unsigned neg = 0;
-      const double* zt = tile + (size_t)(warp * (SCAN_L / 4)) * SCAN_COLS + lane;
-      const double* wt = swt + warp * (SCAN_L / 4);
-#pragma unroll 4
-      for (int r = 0; r < SCAN_L / 4; r += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double z = zt[(size_t)(r + u) * SCAN_COLS];
-          const double t = __dmul_rn(z, wt[r + u]);
-          const double q = __dmul_rn(t, z);
-          S[u] = __dadd_rn(S[u], t);
-          A[u] = __dadd_rn(A[u], fabs(t));
-          Q[u] = __dadd_rn(Q[u], fabs(q));
-          neg |= (unsigned)(__double2hiint(q) & 0x80000000);
-        }
-      }
-      __syncthreads();                                     // misc[1] cleared
-      red[(warp * 3 + 0) * 32 + lane] = (S[0] + S[1]) + (S[2] + S[3]);
-      red[(warp * 3 + 1) * 32 + lane] = (A[0] + A[1]) + (A[2] + A[3]);
-      red[(warp * 3 + 2) * 32 + lane] = (Q[0] + Q[1]) + (Q[2] + Q[3]);
-      if (neg) atomicOr(&misc[1], 1u << lane);
-    }
-    __syncthreads();
-
-    // ---- 2. look-back (warp 0; lane = column for values, lane = predecessor for status words) ----------------------
-    if (warp == 0) {
-      double a[3];
-#pragma unroll
-      for (int v = 0; v < 3; ++v) a[v] = (red[(0 * 3 + v) * 32 + lane] + red[(1 * 3 + v) * 32 + lane]) + (red[(2 * 3 + v) * 32 + lane] + red[(3 * 3 + v) * 32 + lane]);
-      // q = rn(rn(w z) z) is non-negative unless a weight is negative (fit rejects those): then the squares chain is never fast
-      if ((misc[1] >> lane) & 1u) a[2] = __longlong_as_double(0x7ff8000000000000LL);
-      const int64_t c = c0 + lane;
-      const size_t base = ((size_t)seq * sp.max_segs) * 96;
-      double* myagg = lk.agg + base + (size_t)seg * 96;
-      double* myinc = lk.inc + base + (size_t)seg * 96;
-      int* st = lk.status + (size_t)seq * sp.max_segs;
-      double e[3] = {0.0, 0.0, 0.0};
-      if (seg == 0) {
-        if (p.accumulate && c < p.K + p.M) { e[0] = p.sum_z[c]; e[2] = p.sumsq_z[c]; }   // chunked fit: the chains continue
-      } else {
-#pragma unroll
-        for (int v = 0; v < 3; ++v) __stcg(myagg + v * 32 + lane, a[v]);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_gpu(st + seg, 1);
-        int64_t j = seg - 1;                     // nearest predecessor not yet added
-        unsigned long long spins = 0;
-        while (true) {
-          const int64_t pj = j - lane;
-          const int s = pj >= 0 ? ld_acquire_gpu(st + pj) : 3;
-          const unsigned has_inc = __ballot_sync(0xffffffffu, s == 2);
-          const int stop = has_inc ? __ffs(has_inc) - 1 : 32;              // predecessors j .. j - stop (the last one inclusive)
-          const unsigned need = stop >= 31 ? 0xffffffffu : ((2u << stop) - 1u);
-          const unsigned ready = __ballot_sync(0xffffffffu, s != 0);
-          if ((ready & need) != need) {
-            if (++spins > (1ull << 24)) __trap();                          // a lost predecessor must not hang the GPU
-            __nanosleep(40);
-            continue;
-          }
-          __threadfence();
-          const int last = has_inc ? stop : 31;
-          for (int k0 = 0; k0 <= last; k0 += 8) {
-            double v[8][3];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int k = k0 + u;
-              const bool on = k <= last && j - k >= 0;
-              const double* src = ((has_inc && k == stop) ? lk.inc : lk.agg) + base + (size_t)(on ? j - k : 0) * 96;
-#pragma unroll
-              for (int w3 = 0; w3 < 3; ++w3) v[u][w3] = on ? __ldcg(src + w3 * 32 + lane) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-              for (int w3 = 0; w3 < 3; ++w3) e[w3] += v[u][w3];
-          }
-          if (has_inc) break;
-          j -= 32;
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < 3; ++v) { ex[v * 32 + lane] = e[v]; segs[v * 32 + lane] = a[v]; __stcg(myinc + v * 32 + lane, e[v] + a[v]); }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release_gpu(st + seg, 2);
-    }
-    __syncthreads();
-
-    // ---- 3a. proxy starts (threads 0..63: chain = warp, column = lane; same test as k_scan_prefix) ------------------
-    if (warp < 2) {
-      const int chain = warp;
-      const double Pj = chain == 0 ? ex[lane] : ex[64 + lane];
-      const double totj = chain == 0 ? ex[32 + lane] : ex[64 + lane];
-      const double Aj = chain == 0 ? segs[32 + lane] : segs[64 + lane];
-      const double A1 = Aj * (1.0 + 0x1p-20);
-      const double margin = 0x1p-24 * fabs(totj) + 0x1p-40 * fabs(Pj);
-      const double lo = (Pj - A1) - margin, hi = (Pj + A1) + margin;
-      const long long blo = __double_as_longlong(lo), bhi = __double_as_longlong(hi);
-      const int elo = (int)((blo >> 52) & 0x7ff), ehi = (int)((bhi >> 52) & 0x7ff);
-      const bool same = ((blo ^ bhi) >= 0) && elo == ehi && elo >= 1 && elo <= 2046;
-      double B = 0.0;
-      if (Aj == 0.0) B = -0.0;                                                          // only zeros: s + (+-0)
-      else if (same) B = __longlong_as_double((blo & (long long)0xfff0000000000000ULL) | 0x0008000000000000LL);
-      if (c0 + lane >= p.K + p.M) B = 0.0;
-      prox[chain * 32 + lane] = B;
-    }
-    __syncthreads();
-
-    // ---- 3b. proxy chains from shared memory: warp = (chain, parity), lane = column --------------------------------
-    {
-      const int chain = warp >> 1, parity = warp & 1;
-      const double B = prox[chain * 32 + lane];
-      const long long bb = __double_as_longlong(B);
-      const bool slow = bb == 0;
-      const bool ident = bb == (long long)0x8000000000000000ULL;
-      const double start = (parity && !ident) ? __longlong_as_double(bb | 1) : B;
-      double acc = start;
-      const double* zt = tile + lane;
-      if (!__all_sync(0xffffffffu, slow)) {
-        if (cnt == SCAN_L) {
-#pragma unroll 2
-          for (int r = 0; r < SCAN_L; r += 8) {
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const double z = zt[(size_t)(r + u) * SCAN_COLS];
-              t[u] = __dmul_rn(z, swt[r + u]);
-              if (chain) t[u] = __dmul_rn(t[u], z);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t[u]);
-          }
-        } else {
-          for (int r = 0; r < cnt; ++r) {
-            const double z = zt[(size_t)r * SCAN_COLS];
-            double t = __dmul_rn(z, swt[r]);
-            if (chain) t = __dmul_rn(t, z);
-            acc = __dadd_rn(acc, t);
-          }
-        }
-      }
-      const int64_t c = c0 + lane;
-      if (c < p.K + p.M) {
-        double d = ident ? acc : __dsub_rn(acc, start);
-        if (slow) d = __longlong_as_double((long long)SCAN_SLOW_MARK);
-        scan_plane(sp, f, chain, parity, c)[seg] = d;
-      }
-    }
-    cur = nxt;
-    buf ^= 1;
-  }
-}
-
-// Ascending list of the slow segments of every (fold, chain, column) from the marks k_scan_fused left in the d0 plane;
-// groups that are mostly slow (or too short to be worth it) are handed back to k_moments_pipe.  One warp per column chain.
-__global__ void __launch_bounds__(128) k_scan_lists(ScanParams sp, int mine) {
-  const MomentParams<double>& p = sp.p;
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);        // (own group, column, chain)
-  const int64_t f = blockIdx.y;
-  if (wid >= (int64_t)mine * SCAN_COLS * 2) return;
-  const int chain = (int)(wid & 1), col = (int)((wid >> 1) % SCAN_COLS), gi = (int)(wid / (2 * SCAN_COLS));
-  const int g = p.grp0 + gi * p.grp_stride;
-  const int64_t c = (int64_t)g * SCAN_COLS + col;
-  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
-  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
-  const int64_t nseg = (n + sp.L - 1) / sp.L;
-  int* okp = sp.ok + f * sp.groups_total + g;
-  if (nseg < 4 && lane == 0) atomicAnd(okp, 0);
-  if (c >= p.K + p.M) return;
-  const double* d0 = scan_plane(sp, f, chain, 0, c);
-  int* list = sp.slow_list + ((size_t)(f * 2 + chain) * p.ld + c) * sp.slow_cap;
-  int nslow = 0;
-  for (int64_t J = 0; J < nseg; J += 32) {
-    const int64_t j = J + lane;
-    const bool slow = j < nseg && (unsigned long long)__double_as_longlong(d0[j]) == SCAN_SLOW_MARK;
-    const unsigned m = __ballot_sync(0xffffffffu, slow);
-    if (slow) {
-      const int pos = nslow + __popc(m & ((1u << lane) - 1u));
-      if (pos < sp.slow_cap) list[pos] = (int)j;
-    }
-    nslow += __popc(m);
-  }
-  if (lane == 0) {
-    sp.slow_cnt[(size_t)(f * 2 + chain) * p.ld + c] = nslow;
-    if (nslow > nseg / 4 || nslow > sp.slow_cap) atomicAnd(okp, 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t f = blockIdx.z;
+  const int64_t c = (int64_t)(p.grp0 + blockIdx.x * p.grp_stride) * SCAN_COLS + lane;
+  const int64_t beg = p.offsets[p.fold0 + f];
+  const int64_t n = p.offsets[p.fold0 + f + 1] - beg;
+  const int64_t* idx = p.indices + beg;
+  if (blockIdx.y == 0 && threadIdx.x == 0) sp.ok[f * sp.groups_total + p.grp0 + blockIdx.x * p.grp_stride] = 1;   // pass 2 clears it
+  const bool live = c < p.K + p.M;
+  const double tot_s = live ? p.sum_z[c] : 0.0, tot_q = live ? p.sumsq_z[c] : 0.0;
+  const double invN = 1.0 / (double)p.N;
+  for (int64_t s = (int64_t)blockIdx.y * SCAN_WARPS + warp; s * sp.L < n; s += (int64_t)gridDim.y * SCAN_WARPS) {
+    const int64_t r0 = s * sp.L;
+    const int cnt = (int)min((int64_t)sp.L, n - r0);
+    const double frac = ((double)r0 + 0.5 * (double)cnt) * invN;
+    const double Bs = scan_guess_proxy(tot_s * frac), Bq = scan_guess_proxy(tot_q * frac);
+    const long long bs = __double_as_longlong(Bs), bq = __double_as_longlong(Bq);
+    const double Bs1 = bs ? __longlong_as_double(bs | 1) : 0.0, Bq1 = bq ? __longlong_as_double(bq | 1) : 0.0;
+    double S = 0.0, A = 0.0, Q = 0.0, c0 = Bs, c1 = Bs1, e0 = Bq, e1 = Bq1;
+    unsigned negq = 0, all_neg_t = 0x80000000u, all_neg_q = 0x80000000u;
+    scan_rows(p, idx, r0, cnt, lane, p.Z + c, [&](double t, double q) {
+      S = __dadd_rn(S, t);
+      A = __dadd_rn(A, fabs(t));
+      Q = __dadd_rn(Q, fabs(q));
+      c0 = __dadd_rn(c0, t);
+      c1 = __dadd_rn(c1, t);
+      e0 = __dadd_rn(e0, q);
+      e1 = __dadd_rn(e1, q);
+      const unsigned st = (unsigned)__double2hiint(t), sq = (unsigned)__double2hiint(q);
+      negq |= sq & 0x80000000u;
+      all_neg_t &= st;
+      all_neg_q &= sq;
+    });
+    scan_plane(sp, f, 0, 0, c)[s] = S;
+    scan_plane(sp, f, 0, 1, c)[s] = A;
+    scan_plane(sp, f, 1, 0, c)[s] = Q;
+    scan_plane(sp, f, 1, 1, c)[s] = negq ? __longlong_as_double(0x7ff8000000000000LL) : Q;
+    // a segment that holds only zeros adds (+-0) to the running sum: its increment is -0 iff every term is -0
+    const bool zs = A == 0.0, zq = Q == 0.0 && !negq;
+    const double ids = (all_neg_t & 0x80000000u) ? -0.0 : 0.0, idq = (all_neg_q & 0x80000000u) ? -0.0 : 0.0;
+    scan_spec_plane(sp, spec, f, 0, 0, c)[s] = zs ? -0.0 : Bs;
+    scan_spec_plane(sp, spec, f, 0, 1, c)[s] = zs ? ids : __dsub_rn(c0, Bs);
+    scan_spec_plane(sp, spec, f, 0, 2, c)[s] = zs ? ids : __dsub_rn(c1, Bs1);
+    scan_spec_plane(sp, spec, f, 1, 0, c)[s] = zq ? -0.0 : Bq;
+    scan_spec_plane(sp, spec, f, 1, 1, c)[s] = zq ? idq : __dsub_rn(e0, Bq);
+    scan_spec_plane(sp, spec, f, 1, 2, c)[s] = zq ? idq : __dsub_rn(e1, Bq1);
   }
 }
 

@@ -69,12 +69,13 @@ def test_scan_equals_chain_and_oracle_friendly(weighted):
             assert _same(got, want)
 
 
-@pytest.mark.parametrize("fused", ["1", "0"])
-def test_scan_adversarial_columns_bit_exact(fused, monkeypatch):
-    """fused = "1": passes 1 - 3 in one read of the rows (k_scan_fused, decoupled look-back); "0": the four-pass form."""
+@pytest.mark.parametrize("spec", ["1", "0"])
+def test_scan_adversarial_columns_bit_exact(spec, monkeypatch):
+    """spec = "1": fold statistics run passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec), verified
+    by the prefix pass; "0": the four-pass form everywhere."""
     from cvmatrix_b200 import CVMatrix
 
-    monkeypatch.setenv("CVMX_SCAN_FUSED", fused)   # read by cvmx_create
+    monkeypatch.setenv("CVMX_SCAN_SPEC", spec)   # read by cvmx_create
 
     N = 60_000
     A = _adversarial(N)
