@@ -103,7 +103,7 @@ struct cvmx_handle {
   bool filling = false;
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
-  DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look;
+  DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look, peer_sum;
   int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
   int64_t scan_launches = 0;
   int64_t launches = 0;
@@ -1092,7 +1092,7 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
 
 template <typename T>
 int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy,
-                       const double* const* peers = nullptr, int npeers = 0);
+                       const double* const* peers = nullptr, int npeers = 0, bool compact = false);
 
 // ---- folds -----------------------------------------------------------------------------------------
 // Runs folds [f0, f1) of the CSR (d_off/d_idx on device, off on host) and leaves results in device
@@ -1319,18 +1319,20 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
 // the fold of the batch that gram[0] belongs to (a rank may finish only the folds it owns)
 template <typename T>
 int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint32_t want, const double* gram, T* oxx, T* oxy,
-                       const double* const* peers, int npeers) {
+                       const double* const* peers, int npeers, bool compact) {
+  // compact: `gram` holds only folds [f0, f1) (slot f - f0) instead of the whole batch (slot f - batch_f0)
   const int64_t Pn = f1 - f0;
   if (Pn <= 0) return CVMX_OK;
   TableCache& tc = h->tc_finish;
-  const std::vector<int64_t> key = {batch_f0, f0, f1, (int64_t)want, h->csr_version};
+  const std::vector<int64_t> key = {batch_f0, f0, f1, (int64_t)want, h->csr_version, compact ? 1 : 0};
   if (tc.key != key) {
     Plan pl;
     plan_tiles(h, want, pl.tiles);
     pl.fold_units.assign(f1 - batch_f0, 0);
     for (int64_t f = batch_f0; f < f1; ++f) {
       GramUnit u;
-      u.row_begin = u.row_end = 0; u.fold = (int32_t)(f - batch_f0); u.split = 0; u.nsplit = 1; u.part_base = (int32_t)(f - batch_f0);
+      u.row_begin = u.row_end = 0; u.fold = (int32_t)(f - batch_f0); u.split = 0; u.nsplit = 1;
+      u.part_base = (int32_t)(compact ? std::max<int64_t>(f - f0, 0) : f - batch_f0);
       pl.fold_units[f - batch_f0] = (int32_t)pl.units.size();
       pl.units.push_back(u);
       if (f >= f0) pl.split_folds.push_back((int32_t)(f - batch_f0));
@@ -1528,7 +1530,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   if (!h) return CVMX_OK;
   DeviceGuard guard__(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->w_glob, &h->g_off, &h->g_idx, &h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+  for (DevBuf* b : {&h->peer_sum, &h->w_glob, &h->g_off, &h->g_idx, &h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
@@ -1812,9 +1814,21 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
     h->launches++;
     CU(h, cudaGetLastError());
   }
-  int32_t rc = sharded_finish<double>(h, batch_f0, f0, f1, want, (const double*)peer_bufs[0], (double*)oxx, (double*)oxy,
-                                      (const double* const*)peer_bufs, n_peers);
-  if (rc || f1 == f0) return rc;
+  if (f1 == f0) return CVMX_OK;
+  // the owned folds' raw Grams: sum of the peers' buffers at NVLink bandwidth, then the ordinary local epilogue
+  std::vector<int2> tiles;
+  plan_tiles(h, want, tiles);
+  const int64_t per_fold = (int64_t)tiles.size() * GACC * GTHREADS, nsum = (f1 - f0) * per_fold;
+  CU(h, h->peer_sum.reserve((size_t)nsum * sizeof(double)));
+  PeerList pg8;
+  for (int q = 0; q < 8; ++q) pg8.p[q] = q < n_peers ? (const double*)peer_bufs[q] : nullptr;
+  const int ev0 = prof_mark(h);
+  k_peer_sum_frags<<<(unsigned)((nsum / 2 + 255) / 256), 256, 0, h->stream>>>(pg8, n_peers, (f0 - batch_f0) * per_fold, nsum, h->peer_sum.as<double>());
+  h->launches++;
+  prof_span(h, PROF_REDUCE, ev0, prof_mark(h));
+  CU(h, cudaGetLastError());
+  int32_t rc = sharded_finish<double>(h, batch_f0, f0, f1, want, h->peer_sum.as<double>(), (double*)oxx, (double*)oxy, nullptr, 0, true);
+  if (rc) return rc;
   const size_t sz = 8;
   const int64_t C = h->K + h->M, d = f0 - batch_f0, Pn = f1 - f0;
   if (ostats)

@@ -187,9 +187,9 @@ def test_midsize_multi_tile_vs_oracle(dtype, weighted):
                 assert e_us <= 1.5 * e_ref + 1e-5, (key, e_us, e_ref)
                 assert rel_fro(got, ref32) <= 2.5 * e_ref + 1e-5, (key, rel_fro(got, ref32), e_ref)
         assert np.array_equal(XTX, XTX.T)
-        # the batched launch and the per-call launch agree bit for bit (same kernels, same split plan
-        # for a single fold is not guaranteed -> compare to tolerance)
-        assert rel_fro(batch["XTX"][pos], XTX) <= 1e-13 and rel_fro(batch["XTY"][pos], XTY) <= 1e-13
+        # the batched launch and the per-call launch use the same kernels but not the same row-split plan (the plan
+        # depends on how many folds share the launch), so they agree to the tolerance, not bit for bit
+        assert rel_fro(batch["XTX"][pos], XTX) <= tol and rel_fro(batch["XTY"][pos], XTY) <= (tol if dtype == np.float64 else 1e-4)
         assert np.array_equal(batch["X_mean"][pos], stats[0]) and np.array_equal(batch["Y_std"][pos], stats[3])
     if dtype == np.float32:
         key = list(part.folds_dict)[1]
