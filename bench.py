@@ -135,7 +135,8 @@ def config_dict(cfg, world):
            else f"fold-sharded x{world}")
     return {"workload": cfg["name"], "N": N, "K": K, "M": M, "folds": P, "parallelism": par,
             "l2_policy": ("inputs (4.09 GB) larger than L2; no flush needed" if N * K * 8 > 2e8
-                          else "inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2"),
+                          else ("inputs smaller than L2 (LOO): outputs (>=8 GB per step) stream through L2" if P > 1000
+                                else "self-test shape: inputs smaller than L2")),
             "step": "batched fold path over all folds, inputs resident in HBM, outputs to HBM"}
 
 

@@ -8,6 +8,7 @@
 
 #include "../../include/cvmx.h"
 #include "kernels_gram.cuh"
+#include "kernels_gram_tc.cuh"
 #include "kernels_stats.cuh"
 #include "kernels_scan.cuh"
 #include <cstdlib>
@@ -104,6 +105,8 @@ struct cvmx_handle {
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
   DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look, peer_sum;
+  int f32_tc = 1;       // float32 Gram kernel: 1 tcgen05 / tensor memory (k_gram_tc), 0 mma.sync TF32 (k_gram<float>); CVMX_F32_TC
+  bool attr_tc = false;
   int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
   int64_t scan_launches = 0;
   int64_t launches = 0;
@@ -309,6 +312,26 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
   sort_units_longest_first(pl);
 }
 
+// The Gram kernel of the model dtype: float64 -> k_gram<double> (DMMA); float32 -> k_gram_tc (tcgen05 / tensor memory) or
+// k_gram<float> (mma.sync TF32).  gp.fmap must say which of the two float32 kernels writes the accumulators.
+template <typename T> int fmap_of(const cvmx_t* h) { return (sizeof(T) == 4 && h->f32_tc) ? 1 : 0; }
+
+template <typename T>
+int32_t launch_k_gram(cvmx_t* h, unsigned grid, const GramParams<T>& gp) {
+  if constexpr (sizeof(T) == 4) {
+    if (h->f32_tc) {
+      if (!h->attr_tc) {
+        CU(h, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem_bytes()));
+        h->attr_tc = true;
+      }
+      k_gram_tc<<<grid, GLAUNCH, gram_tc_smem_bytes(), h->stream>>>(gp);
+      return CVMX_OK;
+    }
+  }
+  k_gram<T><<<grid, GLAUNCH, gram_smem_bytes<T>(), h->stream>>>(gp);
+  return CVMX_OK;
+}
+
 template <typename T>
 int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const EpiParams<T>& epi,
                     cudaEvent_t stats_ready = nullptr) {
@@ -326,6 +349,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
     CU(h, cudaMemcpyAsync(h->split_folds.p, pl.split_folds.data(), pl.split_folds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   }
   GramParams<T> gp;
+  gp.fmap = fmap_of<T>(h);
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld;
   gp.indices = d_indices;
   gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
@@ -343,7 +367,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   const bool all_split = pl.split_folds.size() == pl.fold_units.size();
   if (stats_ready && !all_split) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));  // fused epilogues read the statistics
   const int ev0 = prof_mark(h);
-  k_gram<T><<<(unsigned)grid, GLAUNCH, smem, h->stream>>>(gp);
+  { int32_t rk = launch_k_gram<T>(h, (unsigned)grid, gp); if (rk) return rk; }
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
@@ -794,6 +818,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       CU(h, cudaMemcpyAsync(h->chunk_ranges.p, h_ranges.data(), h_ranges.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     }
     GramParams<T> gp;
+    gp.fmap = fmap_of<T>(h);
     gp.Z = Z; gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = fused ? h->d_idx.as<int64_t>() : nullptr;
     gp.ntiles = ntiles; gp.raw_out = nullptr; gp.force_partials = 1; gp.epi = epi;
     const size_t smem = gram_smem_bytes<T>();
@@ -851,7 +876,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
       if (nu > 0) {
         gp.units = h->units.as<GramUnit>() + chunk_unit0[c];
         const int ev0 = prof_mark(h);
-        k_gram<T><<<(unsigned)(nu * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+        { int32_t rk = launch_k_gram<T>(h, (unsigned)(nu * ntiles), gp); if (rk) return rk; }
         h->launches++;
         prof_span(h, PROF_GRAM, ev0, prof_mark(h));
       }
@@ -1010,13 +1035,14 @@ int32_t fit_rows_impl(cvmx_t* h, int64_t row0, int64_t nr, const void* X, int64_
   }
   CU(h, cudaMemcpyAsync(h->units.p, units.data(), units.size() * sizeof(GramUnit), cudaMemcpyHostToDevice, h->stream));
   GramParams<T> gp;
+  gp.fmap = fmap_of<T>(h);
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
   gp.units = h->units.as<GramUnit>() + 1; gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = h->partials.as<double>(); gp.raw_out = nullptr; gp.force_partials = 1;
   gp.epi = EpiParams<T>();
   const size_t smem = gram_smem_bytes<T>();
   const int ev0 = prof_mark(h);
-  k_gram<T><<<(unsigned)(nu * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+  { int32_t rk = launch_k_gram<T>(h, (unsigned)(nu * ntiles), gp); if (rk) return rk; }
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
   // accumulator (slot 0) += the block's partials, in place
@@ -1061,6 +1087,7 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
   epi.out_xx = h->Ttot.as<T>(); epi.xx_pitch = ld; epi.xx_stride = 0;
   epi.out_xy = h->Ttot.as<T>() + K; epi.xy_pitch = ld; epi.xy_stride = 0;
   GramParams<T> gp;
+  gp.fmap = fmap_of<T>(h);
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = ld; gp.indices = nullptr;
   gp.units = h->units.as<GramUnit>(); gp.tiles = h->tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = h->partials.as<double>(); gp.raw_out = nullptr; gp.force_partials = 0; gp.epi = epi;
@@ -1286,6 +1313,7 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
   const bool direct = tc.n_partial_units == Pn;     // one unit per fold: k_gram writes the fold's raw Gram itself
   if (!direct) CU(h, h->partials.reserve((size_t)tc.n_partial_units * ntiles * GACC * GTHREADS * sizeof(double)));
   GramParams<T> gp;
+  gp.fmap = fmap_of<T>(h);
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = h->d_idx.as<int64_t>();
   gp.units = tc.units.as<GramUnit>(); gp.tiles = tc.tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = direct ? out : h->partials.as<double>(); gp.raw_out = out; gp.force_partials = 1;
@@ -1297,7 +1325,7 @@ int32_t sharded_gram(cvmx_t* h, int64_t f0, int64_t f1, uint32_t want, int shard
     h->attr_gram = true;
   }
   const int ev0 = prof_mark(h);
-  k_gram<T><<<(unsigned)(tc.n_units * ntiles), GLAUNCH, smem, h->stream>>>(gp);
+  { int32_t rk = launch_k_gram<T>(h, (unsigned)(tc.n_units * ntiles), gp); if (rk) return rk; }
   h->launches++;
   const int ev1 = prof_mark(h);
   prof_span(h, PROF_GRAM, ev0, ev1);
@@ -1349,6 +1377,7 @@ int32_t sharded_finish(cvmx_t* h, int64_t batch_f0, int64_t f0, int64_t f1, uint
   epi.out_xx = oxx ? oxx - (f0 - batch_f0) * h->K * h->K : nullptr; epi.xx_pitch = h->K; epi.xx_stride = h->K * h->K;
   epi.out_xy = oxy ? oxy - (f0 - batch_f0) * h->K * h->M : nullptr; epi.xy_pitch = h->M; epi.xy_stride = h->K * h->M;
   GramParams<T> gp;
+  gp.fmap = fmap_of<T>(h);
   gp.Z = h->Z.as<T>(); gp.w = h->w.as<T>(); gp.ld = h->ld; gp.indices = nullptr;
   gp.units = tc.units.as<GramUnit>(); gp.tiles = tc.tiles.as<int2>(); gp.ntiles = ntiles;
   gp.partials = const_cast<double*>(gram); gp.raw_out = nullptr; gp.force_partials = 0;
@@ -1502,6 +1531,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_SCAN_SPEC")) h->scan_spec = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_F32_TC")) h->f32_tc = std::atoi(e) ? 1 : 0;
   DeviceGuard guard__(device);
   if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;

@@ -77,6 +77,9 @@ struct GramParams {
   // peers', mapped over NVLink (symmetric memory) - and the owner sums them on the fly instead of an all-reduce
   const double* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int npeers = 0;
+  // float32 only: which kernel produced the accumulators, i.e. which (row, column) a thread's 64 values belong to
+  //   0  k_gram<float>   (mma.sync m16n8k8 fragments)      1  k_gram_tc   (tensor-memory lanes: thread = output row)
+  int fmap = 0;
 };
 
 // float32 models run the contraction on the TF32 tensor cores (3xTF32 split, float32 accumulators in registers) and keep
@@ -102,7 +105,7 @@ constexpr int GFLUSH = 4;   // float32: stages (of GBK rows) between two flushes
 //          result is exactly symmetric) and, for off-diagonal tiles, the mirrored XTX block.
 template <typename T>
 __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, const EpiParams<T>& e, int fold, int bi,
-                                              int bj) {
+                                              int bj, int fmap = 0) {
   constexpr int CP = GramCfg<T>::CPITCH;
   typedef typename GramCfg<T>::vec2 vec2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -124,6 +127,17 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
         *reinterpret_cast<vec2*>(sC + r * CP + cb + 2) = hi;
       }
     }
+  } else if (fmap == 1) {
+    // float32 from tensor memory (k_gram_tc): thread = output row 32 (warp % 4) + lane, linear index = column - 64 (warp / 4)
+    const int r = 32 * (warp & 3) + lane, cb = 64 * (warp >> 2);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vec2 v;
+        v.x = (T)acc[t][u][0]; v.y = (T)acc[t][u][1];
+        *reinterpret_cast<vec2*>(sC + r * CP + cb + (t * 4 + u) * 2) = v;
+      }
   } else {
     // float32: the accumulators follow the m16n8k8 fragment layout.  Linear index ((t * 4 + u) * 2 + e) = mt * 16 + nt * 4 + c
     // with m-tile mt, n-tile nt and C-fragment register c: row = 16 mt + g + 8 (c / 2), column = 8 nt + 2 q + (c % 2).
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gram_reduce(const GramParams<T>
       }
     return;
   }
-  gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, tl.x, tl.y);
+  gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, tl.x, tl.y, p.fmap);
 }
 
 // Row-split partials of (fold, tile) summed in split order into raw fragment buffers, element-parallel: the sharded

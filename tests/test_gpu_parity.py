@@ -417,7 +417,9 @@ def test_wide_k_and_m_multi_tile(dtype):
     # XTY only / XTX only take the reduced tile sets
     xty, _ = m.training_XTY(part.get_validation_indices(3))
     xtx, _ = m.training_XTX(part.get_validation_indices(3))
-    assert rel_fro(xty, out["XTY"][3]) <= 1e-13 and rel_fro(xtx, out["XTX"][3]) <= 1e-13
+    # (a single fold is planned differently from a batch of ten: the same kernels in another summation order)
+    same = 1e-13 if dtype == np.float64 else 1e-6
+    assert rel_fro(xty, out["XTY"][3]) <= same and rel_fro(xtx, out["XTX"][3]) <= same
 
 
 def test_pickle_roundtrip_and_abi_misuse():

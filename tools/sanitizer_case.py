@@ -45,6 +45,24 @@ def case(N, K, M, P, tag, seed=42, scan=None, loo_mode=None, fused=False):
         assert np.array_equal(a, b), tag
 
 
+def case_f32(N, K, M, P, tag):
+    """float32 model, un-centred (the regime where numpy-float32 is accurate to 1e-5): the TF32 tensor-core Gram kernels."""
+    X, Y, w, folds = make_inputs(N, K, M, P, dtype=np.float32, seed=9)
+    orc = OracleCVMatrix(False, False, False, False, dtype=np.float32)
+    orc.fit(X, Y, w)
+    m = CVMatrix(False, False, False, False, dtype=np.float32)
+    m.fit(X, Y, w)
+    e = rel_fro(m.XTX, orc.XTX)
+    print("f32 totals relFro", e, flush=True)
+    assert e <= 1e-5, tag
+    part = Partitioner(folds)
+    m.set_folds(part)
+    out = m.training_batch()
+    r = orc.fold(part.get_validation_indices(0))
+    assert rel_fro(out["XTX"][0], r.XTX) <= 1e-5 and rel_fro(out["XTY"][0], r.XTY) <= 1e-5, tag
+    print("ok", tag, flush=True)
+
+
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "cfg1"):
     case(100, 50, 10, 5, "cfg1 README quick-start")
@@ -61,4 +79,6 @@ if which in ("all", "few"):
     case(600, 70, 3, 100, "leave-few-out (6 rows per fold)", seed=6)
 if which in ("all", "fused"):
     case(5000, 40, 3, 4, "fused fit + folds", seed=7, fused=True)
+if which in ("all", "f32"):
+    case_f32(3000, 200, 5, 3, "float32 model (TF32 tensor cores)")
 print("SANITIZER_CASES_OK", which)
