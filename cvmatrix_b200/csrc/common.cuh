@@ -88,15 +88,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
       : "d"(a), "d"(b));
 }
 
-// ---- TF32 tensor-core MMA (float32 models): D(16x8, f32) += A(16x8, row) * B(8x8, col) ---------------------------
-// Lane l (g = l / 4, q = l % 4) holds A[g][q], A[g+8][q], A[g][q+4], A[g+8][q+4]; B[q][g], B[q+4][g];
-// C/D[g][2q], [g][2q+1], [g+8][2q], [g+8][2q+1].  Operands are float32 bit patterns of which the tensor core reads the
-// upper 19 bits (10-bit mantissa); the 3xTF32 split in kernels_gram.cuh recovers float32 products from them.
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 // x = hi + lo with hi = x rounded to TF32 (round to nearest) and lo = x - hi (exact in float32)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hi) : "f"(x));

@@ -105,7 +105,12 @@ struct cvmx_handle {
   int64_t fill_units_cap = 0, fill_calls = 0;
   DevBuf ystage;
   DevBuf scan_seg, scan_ok, scan_list, scan_cnt, scan_look, peer_sum;
-  int f32_tc = 1;       // float32 Gram kernel: 1 tcgen05 / tensor memory (k_gram_tc), 0 mma.sync TF32 (k_gram<float>); CVMX_F32_TC
+  // float32 Gram kernel (CVMX_F32_TC): 1 = k_gram_tc (tcgen05 kind::tf32, 3xTF32, ~3e-7 of the raw products) for wide models
+  // (K (K + M) >= F32_TC_MIN_WIDTH, the tensor-core-bound regime), k_gram<float> (float64 accumulation on the DMMA pipe) for
+  // narrow ones; 0 = always k_gram<float>; 2 = always k_gram_tc.  Decided once per fit (fmap): every raw fragment buffer
+  // of a handle - partials, kept fold Grams, the buffers ranks exchange - then has ONE layout, on every rank.
+  int f32_tc = 1;
+  int fmap = 0;
   bool attr_tc = false;
   int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
   int64_t scan_launches = 0;
@@ -314,12 +319,19 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
 
 // The Gram kernel of the model dtype: float64 -> k_gram<double> (DMMA); float32 -> k_gram_tc (tcgen05 / tensor memory) or
 // k_gram<float> (mma.sync TF32).  gp.fmap must say which of the two float32 kernels writes the accumulators.
-template <typename T> int fmap_of(const cvmx_t* h) { return (sizeof(T) == 4 && h->f32_tc) ? 1 : 0; }
+// Narrow float32 models stay on the float64-accumulating kernel: they are not tensor-core-bound, and on cancellation-sensitive
+// small cases (centred matrices of a few hundred rows and a handful of columns) float64 accumulation reproduces numpy-float32
+// to its own rounding, which the 3xTF32 products (2^-22 per product) do not.
+constexpr double F32_TC_MIN_WIDTH = 65536.0;   // K (K + M): K >~ 256
+template <typename T> int fmap_of(const cvmx_t* h) { return sizeof(T) == 4 ? h->fmap : 0; }
+template <typename T> void choose_fmap(cvmx_t* h, int64_t K, int64_t M) {
+  h->fmap = (sizeof(T) == 4 && (h->f32_tc == 2 || (h->f32_tc == 1 && (double)K * (double)(K + M) >= F32_TC_MIN_WIDTH))) ? 1 : 0;
+}
 
 template <typename T>
 int32_t launch_k_gram(cvmx_t* h, unsigned grid, const GramParams<T>& gp) {
   if constexpr (sizeof(T) == 4) {
-    if (h->f32_tc) {
+    if (gp.fmap == 1) {
       if (!h->attr_tc) {
         CU(h, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem_bytes()));
         h->attr_tc = true;
@@ -644,6 +656,7 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
   h->fitted = false; h->filling = false; h->slab = false;
+  choose_fmap<T>(h, K, M);
   h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = w != nullptr;
   h->P = 0; h->csr_version++; h->plan = Plan();
   CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
@@ -941,6 +954,7 @@ int32_t fit_begin_impl(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weigh
   const size_t sz = sizeof(T);
   const int64_t ld = round_up(K + M, 32);
   h->fitted = false; h->filling = false; h->slab = false;
+  choose_fmap<T>(h, K, M);
   h->N = N; h->K = K; h->M = M; h->ld = ld; h->weighted = weighted != 0;
   h->P = 0; h->csr_version++; h->plan = Plan();
   CU(h, h->Z.reserve((size_t)std::max<int64_t>(N, 1) * ld * sz));
@@ -1531,7 +1545,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_SCAN_SPEC")) h->scan_spec = std::atoi(e) ? 1 : 0;
-  if (const char* e = std::getenv("CVMX_F32_TC")) h->f32_tc = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_F32_TC")) h->f32_tc = std::max(0, std::min(2, std::atoi(e)));
   DeviceGuard guard__(device);
   if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h;

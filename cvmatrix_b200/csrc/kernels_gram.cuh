@@ -77,23 +77,18 @@ struct GramParams {
   // peers', mapped over NVLink (symmetric memory) - and the owner sums them on the fly instead of an all-reduce
   const double* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int npeers = 0;
-  // float32 only: which kernel produced the accumulators, i.e. which (row, column) a thread's 64 values belong to
-  //   0  k_gram<float>   (mma.sync m16n8k8 fragments)      1  k_gram_tc   (tensor-memory lanes: thread = output row)
+  // which kernel produced the accumulators, i.e. which (row, column) a thread's 64 values belong to
+  //   0  k_gram<T>   (DMMA m8n8k4 fragments)      1  k_gram_tc   (float32 only: tensor-memory lanes, thread = output row)
   int fmap = 0;
 };
 
-// float32 models run the contraction on the TF32 tensor cores (3xTF32 split, float32 accumulators in registers) and keep
-// the float64 master accumulators of the tile in shared memory, in front of the ring: GACC x GTHREADS doubles = 128 KB.
-// The same region later serves as the epilogue tile, exactly as the ring does for float64.
-template <typename T> __host__ __device__ constexpr size_t gram_ring_offset() { return sizeof(T) == 4 ? (size_t)GACC * GTHREADS * sizeof(double) : 0; }
 template <typename T>
 __host__ __device__ constexpr size_t gram_smem_bytes() {
   size_t pipe = sizeof(T) * ((size_t)2 * GSTAGES * GBK * GramCfg<T>::PITCH + (size_t)GSTAGES * GBK);
   size_t stage = sizeof(T) * (size_t)GB * GramCfg<T>::CPITCH;
-  size_t body = gram_ring_offset<T>() ? gram_ring_offset<T>() + pipe : (pipe > stage ? pipe : stage);
+  size_t body = (pipe > stage ? pipe : stage);
   return (body + 15) / 16 * 16 + 2 * GSTAGES * sizeof(uint64_t);   // + full / empty mbarriers at the end
 }
-constexpr int GFLUSH = 4;   // float32: stages (of GBK rows) between two flushes of the float32 accumulators into the float64 ones
 
 // Epilogue of one 128 x 128 tile.
 //  pass 1  accumulator fragments -> shared tile sC (raw G, model dtype).  m-tile t covers tile rows
@@ -113,7 +108,19 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
   const int64_t K = e.K, C = e.K + e.M, ld = e.ld;
   const bool diag = bi == bj;
 
-  if constexpr (sizeof(T) == 8) {
+  if (fmap == 1) {
+    // accumulators read from tensor memory (k_gram_tc): thread = output row 32 (warp % 4) + lane, linear index
+    // ((t * 4 + u) * 2 + e) = column - 64 (warp / 4)
+    const int r = 32 * (warp & 3) + lane, cb = 64 * (warp >> 2);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vec2 v;
+        v.x = (T)acc[t][u][0]; v.y = (T)acc[t][u][1];
+        *reinterpret_cast<vec2*>(sC + r * CP + cb + (t * 4 + u) * 2) = v;
+      }
+  } else {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int r = wm * 64 + 16 * (t >> 1) + 2 * g + (t & 1);
@@ -127,30 +134,6 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
         *reinterpret_cast<vec2*>(sC + r * CP + cb + 2) = hi;
       }
     }
-  } else if (fmap == 1) {
-    // float32 from tensor memory (k_gram_tc): thread = output row 32 (warp % 4) + lane, linear index = column - 64 (warp / 4)
-    const int r = 32 * (warp & 3) + lane, cb = 64 * (warp >> 2);
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vec2 v;
-        v.x = (T)acc[t][u][0]; v.y = (T)acc[t][u][1];
-        *reinterpret_cast<vec2*>(sC + r * CP + cb + (t * 4 + u) * 2) = v;
-      }
-  } else {
-    // float32: the accumulators follow the m16n8k8 fragment layout.  Linear index ((t * 4 + u) * 2 + e) = mt * 16 + nt * 4 + c
-    // with m-tile mt, n-tile nt and C-fragment register c: row = 16 mt + g + 8 (c / 2), column = 8 nt + 2 q + (c % 2).
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int lin0 = (t * 4 + u) * 2, mt = lin0 >> 4, nt = (lin0 >> 2) & 3, c0 = lin0 & 3;
-        const int r = wm * 64 + 16 * mt + g + 8 * (c0 >> 1), cb = wn * 32 + 8 * nt + 2 * q;
-        vec2 v;
-        v.x = (T)acc[t][u][0]; v.y = (T)acc[t][u][1];
-        *reinterpret_cast<vec2*>(sC + r * CP + cb) = v;
-      }
   }
   compute_barrier();
 
@@ -266,7 +249,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
   constexpr int PITCH = GramCfg<T>::PITCH;
   typedef typename GramCfg<T>::vec2 vec2;
 
-  T* sA = reinterpret_cast<T*>(smem_raw + gram_ring_offset<T>());
+  T* sA = reinterpret_cast<T*>(smem_raw);
   T* sB = sA + (size_t)GSTAGES * GBK * PITCH;
   T* sW = sB + (size_t)GSTAGES * GBK * PITCH;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + gram_smem_bytes<T>() - 2 * GSTAGES * sizeof(uint64_t));
@@ -350,92 +333,6 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
   const int ewn = helper ? wn + 2 : wn;
   const int my_parity = helper ? 1 : 0;
 
-  if constexpr (sizeof(T) == 4) {
-    // ---- float32: 3xTF32 on the tensor cores -------------------------------------------------------------------
-    // a = rn(w x) and z are split as hi + lo (hi = value rounded to TF32, lo = the exact float32 remainder) and
-    // a z ~= a_hi z_hi + a_hi z_lo + a_lo z_hi (the dropped lo lo term is 2^-22 of the product); the three
-    // mma.sync.m16n8k8.tf32 accumulate in float32 registers, which are added into the float64 master accumulators in
-    // shared memory every GFLUSH stages (64 rows).  The tensor core TRUNCATES its float32 accumulator after every MMA
-    // (a bias of about -2e-8 of the running partial sum per MMA), so the main term a_hi z_hi - 8 MMAs per flush window:
-    // ~2e-7 - and the two small terms (2^-11 of it: their truncation is negligible) are chained in separate accumulators,
-    // and the window is short; the error then does not depend on how long the fold is.
-    // Warp tile 64 x 32 = 4 m-tiles (16 rows) x 4 n-tiles (8 columns).
-    double* sacc = reinterpret_cast<double*>(smem_raw) + tid;     // [GACC][GTHREADS], this thread's column
-#pragma unroll
-    for (int i = 0; i < GACC; ++i) sacc[i * GTHREADS] = 0.0;
-    float facc[4][4][4], fsm[4][4][4];     // main term / small terms
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) facc[mt][nt][c] = fsm[mt][nt][c] = 0.f;
-    int since_flush = 0;
-    auto flush = [&]() {
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double* dst = sacc + (size_t)(mt * 16 + nt * 4 + c) * GTHREADS;
-            *dst += (double)facc[mt][nt][c] + (double)fsm[mt][nt][c];
-            facc[mt][nt][c] = fsm[mt][nt][c] = 0.f;
-          }
-      since_flush = 0;
-    };
-#pragma unroll 1
-    for (int64_t kt = 0; kt < nk; ++kt) {
-      const int slot = (int)(kt % GSTAGES);
-      mbar_wait(full + slot, (unsigned)(kt / GSTAGES) & 1);
-      const float* a_base = reinterpret_cast<const float*>(sA) + (size_t)slot * GBK * PITCH + wm * 64 + g;
-      const float* b_base = reinterpret_cast<const float*>(diag ? sA : sB) + (size_t)slot * GBK * PITCH + ewn * 32 + g;
-      const float* w_base = reinterpret_cast<const float*>(sW) + slot * GBK;
-      const int rows = (int)min((int64_t)GBK, nrows - kt * GBK);
-      if (!(half && (int)(kt & 1) != my_parity)) {
-#pragma unroll
-        for (int ks = 0; ks < GBK / 8; ++ks) {
-          const int k0 = ks * 8 + q, k1 = k0 + 4;
-          const bool ok0 = k0 < rows, ok1 = k1 < rows;       // rows past the end of the unit were never copied
-          const float w0 = ok0 ? w_base[k0] : 0.f, w1 = ok1 ? w_base[k1] : 0.f;
-          uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            const float z0 = ok0 ? b_base[k0 * PITCH + 8 * nt] : 0.f, z1 = ok1 ? b_base[k1 * PITCH + 8 * nt] : 0.f;
-            split_tf32(z0, bh[nt][0], bl[nt][0]);
-            split_tf32(z1, bh[nt][1], bl[nt][1]);
-          }
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            uint32_t ah[4], al[4];
-            const float x00 = ok0 ? a_base[k0 * PITCH + 16 * mt] : 0.f, x10 = ok0 ? a_base[k0 * PITCH + 16 * mt + 8] : 0.f;
-            const float x01 = ok1 ? a_base[k1 * PITCH + 16 * mt] : 0.f, x11 = ok1 ? a_base[k1 * PITCH + 16 * mt + 8] : 0.f;
-            split_tf32(__fmul_rn(x00, w0), ah[0], al[0]);      // rn(w x) in float32 == WX of the reference
-            split_tf32(__fmul_rn(x10, w0), ah[1], al[1]);
-            split_tf32(__fmul_rn(x01, w1), ah[2], al[2]);
-            split_tf32(__fmul_rn(x11, w1), ah[3], al[3]);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              mma_tf32(fsm[mt][nt], al, bh[nt][0], bh[nt][1]);
-              mma_tf32(fsm[mt][nt], ah, bl[nt][0], bl[nt][1]);
-              mma_tf32(facc[mt][nt], ah, bh[nt][0], bh[nt][1]);
-            }
-          }
-        }
-        if (++since_flush == GFLUSH) flush();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + slot);
-    }
-    flush();
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc[t][u][0] = sacc[(size_t)((t * 4 + u) * 2 + 0) * GTHREADS];
-        acc[t][u][1] = sacc[(size_t)((t * 4 + u) * 2 + 1) * GTHREADS];
-      }
-  } else {
 #pragma unroll 1
   for (int64_t kt = 0; kt < nk; ++kt) {
     const int slot = (int)(kt % GSTAGES);
@@ -499,7 +396,6 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + slot);
-  }
   }
   compute_barrier();   // every stage consumed by every compute warp: the ring can be reused as the epilogue tile
 

@@ -7,7 +7,7 @@
 // rounded to TF32 and the lo parts the exact float32 remainders, a z ~= a_lo z_hi + a_hi z_lo + a_hi z_hi (the dropped
 // lo lo term is 2^-22 of the product).  One CTA = one 128 x 128 output tile of one (fold, row-split) unit, as in k_gram:
 //
-//   warps 8-9   producers   TMA bulk copies gather TBK = 32 rows x {A block, B block} (512 bytes per row piece) into a
+//   warps 8-10  producers   TMA bulk copies gather TBK = 32 rows x {A block, B block} (512 bytes per row piece) into a
 //                           staging ring, row weights by cp.async; full / empty mbarriers                       (UBLKCP)
 //   warps 0-7   converters  staging -> UMMA operands: rn(w x) for A, the hi / lo split, and the TRANSPOSE the tensor
 //                           core wants - operands are K-major (K = the data-row index is contiguous: 32 TF32 = one
@@ -20,8 +20,11 @@
 //                           REGISTER accumulators; two TMEM accumulators alternate, so the flush of window w overlaps
 //                           the MMAs of window w + 1                                                         (LDTM)
 //
-// The tensor core accumulates in float32 (and truncates after every MMA), hence the short windows: 128 rows = 16 main-term
-// MMAs per window bound the accumulation error at ~4e-7 of a window's partial sum, independent of the fold length.
+// The tensor core accumulates in float32 and TRUNCATES after every MMA (a bias of about -2e-8 of the accumulator per MMA;
+// measured: 48 MMAs per window into one accumulator gave -1.1e-6), hence (a) short windows for the main term a_hi z_hi -
+// 128 rows = 16 MMAs per window, ~3.5e-7 of a window's partial sum, independent of the fold length - and (b) a SEPARATE
+// accumulator for the two small terms (2^-11 of the main one: their truncation is negligible even over a whole unit), read once
+// at the end.
 // The float64 accumulators leave through the same partial-buffer / epilogue code as every other variant
 // (fragment map 1: thread tid owns output row 32 (warp % 4) + lane and columns 64 (warp / 4) + 0..63).
 #pragma once
@@ -30,12 +33,12 @@
 namespace cvmx {
 
 constexpr int TBK = 32;          // data rows per stage = K extent of one swizzle atom (32 TF32 = 128 bytes)
-constexpr int TSTAGES = 2;       // staging ring depth
+constexpr int TSTAGES = 3;       // staging ring depth (one producer warp per slot)
 constexpr int TOPS = 2;          // operand buffer sets
 constexpr int TFLUSH = 4;        // stages per accumulator window (128 rows)
 constexpr int TOP_BYTES = GB * 128;                       // one operand buffer: 128 rows x 128 bytes = 16 KB
 constexpr int TSTAGE_BYTES = 2 * TBK * GB * 4;            // A rows + B rows of a stage: 32 KB
-constexpr int TMEM_COLS = 256;                            // two 128-column float32 accumulators
+constexpr int TMEM_COLS = 512;                            // float32 accumulators of 128 columns: main term x 2 (windows alternate), small terms x 1
 // (no setmaxnreg split here: the converters' 64 float64 accumulators + conversion temporaries fit the 168 registers the
 // CTA is launched with, and the issuer's descriptor arithmetic does not fit the 64 a trimmed producer warpgroup would keep)
 
@@ -99,9 +102,9 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
   float* s_stage = reinterpret_cast<float*>(smem + (size_t)TOPS * 4 * TOP_BYTES);   // [TSTAGES][A: TBK x 128 | B: TBK x 128]
   float* s_w = s_stage + (size_t)TSTAGES * TSTAGE_BYTES / 4;               // [TSTAGES][TBK]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + TSTAGES * TBK);
-  uint64_t *full_s = bars, *empty_s = bars + 2, *op_full = bars + 4, *op_free = bars + 6, *acc_full = bars + 8, *acc_free = bars + 10;
-  uint64_t* done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t *full_s = bars, *empty_s = bars + 3, *op_full = bars + 6, *op_free = bars + 8, *acc_full = bars + 10, *acc_free = bars + 12;
+  uint64_t* done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % p.ntiles;
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
   const int64_t nwin = (nk + TFLUSH - 1) / TFLUSH;
 
   if (tid == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_s + s, 33); mbar_init(empty_s + s, GTHREADS / 32); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(full_s + s, 33); mbar_init(empty_s + s, GTHREADS / 32);
       mbar_init(op_full + s, GTHREADS / 32); mbar_init(op_free + s, 1);
       mbar_init(acc_full + s, 1); mbar_init(acc_free + s, GTHREADS / 32);
     }
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
     if (warp < 11) {
       // ---------------- producers: lane = row of the stage.  Warp 8 + s owns staging slot s (a slot must have ONE producer:
       // a parity wait can only tell "the previous phase" from "this one", so a third warp sharing two slots would run
-      // two phases ahead and overwrite a stage that has not been consumed); warp 10 has nothing to do. ----------------
+      // two phases ahead and overwrite a stage that has not been consumed). ----------------
       const int64_t acol = (int64_t)bi * GB, bcol = (int64_t)bj * GB;
       const unsigned a_bytes = (unsigned)(min((int64_t)GB, ld - acol) * 4), b_bytes = diag ? 0u : (unsigned)(min((int64_t)GB, ld - bcol) * 4);
       for (int64_t kt = warp - GTHREADS / 32; kt < nk && warp - GTHREADS / 32 < TSTAGES; kt += TSTAGES) {
@@ -167,13 +170,13 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
           const unsigned char* ops = s_ops + (size_t)ob * 4 * TOP_BYTES;
           const uint64_t a_hi = tc_smem_desc(ops), a_lo = tc_smem_desc(ops + TOP_BYTES);
           const uint64_t b_hi = tc_smem_desc(ops + 2 * TOP_BYTES), b_lo = tc_smem_desc(ops + 3 * TOP_BYTES);
-          const uint32_t d = tmem_base + (uint32_t)ab * GB;
+          const uint32_t d = tmem_base + (uint32_t)ab * GB, d_small = tmem_base + 2u * GB;
 #pragma unroll
           for (int ks = 0; ks < TBK / 8; ++ks) {                       // 32 bytes along K per step: address field + 2
             const uint64_t o = (uint64_t)(ks * 2);
-            tc_mma_tf32(d, a_lo + o, b_hi + o, TC_IDESC, (first && ks == 0) ? 0u : 1u);
-            tc_mma_tf32(d, a_hi + o, b_lo + o, TC_IDESC, 1u);
-            tc_mma_tf32(d, a_hi + o, b_hi + o, TC_IDESC, 1u);
+            tc_mma_tf32(d_small, a_lo + o, b_hi + o, TC_IDESC, (kt == 0 && ks == 0) ? 0u : 1u);
+            tc_mma_tf32(d_small, a_hi + o, b_lo + o, TC_IDESC, 1u);
+            tc_mma_tf32(d, a_hi + o, b_hi + o, TC_IDESC, (first && ks == 0) ? 0u : 1u);
           }
           tc_commit(op_free + ob);                                    // operand set reusable when these MMAs have read it
           if ((kt % TFLUSH) == TFLUSH - 1 || kt == nk - 1) tc_commit(acc_full + ab);
@@ -195,11 +198,9 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
 
-  auto flush = [&](int64_t win) {
-    const int ab = (int)(win & 1);
-    mbar_wait_bounded(acc_full + ab, (unsigned)((win / 2) & 1));
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ab * GB + 64 * (warp >> 2));
+  // this thread's 64 values of the accumulator at TMEM column `col0` are added into the float64 registers
+  auto drain = [&](uint32_t col0) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + col0 + (uint32_t)(64 * (warp >> 2));
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       uint32_t r[16];
@@ -211,12 +212,19 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
         acc[lin >> 3][(lin >> 1) & 3][lin & 1] += (double)__uint_as_float(r[j]);
       }
     }
+  };
+  auto flush = [&](int64_t win) {
+    const int ab = (int)(win & 1);
+    mbar_wait_bounded(acc_full + ab, (unsigned)((win / 2) & 1));
+    tc_fence_after();
+    drain((uint32_t)(ab * GB));
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(acc_free + ab);
   };
 
   // thread -> operand row i = tid % 128 (output row of A / column of B) and K chunks rg = tid / 128 + 2 j (4 data rows each)
+  int64_t flushed = 0;
   const int ci = tid & 127, rg0 = tid >> 7;
   const uint32_t op_row = (uint32_t)((ci >> 3) * 1024 + (ci & 7) * 128);
 #pragma unroll 1
@@ -250,10 +258,11 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
     fence_proxy_async();                                               // generic-proxy stores -> the tensor core's async proxy
     __syncwarp();
     if (lane == 0) { mbar_arrive(op_full + ob); mbar_arrive(empty_s + slot); }
-    // flush the previous window while the issuer works on this one (its MMAs have had a whole stage to finish)
-    if ((kt % TFLUSH) == 0 && kt > 0) flush(kt / TFLUSH - 1);
+    // flush finished windows one stage late: the issuer has then had a whole conversion to complete their last MMAs
+    while (kt >= 1 && flushed <= (kt - 1) / TFLUSH - 1) flush(flushed++);
   }
-  if (nk > 0) flush(nwin - 1);
+  while (flushed < nwin) flush(flushed++);
+  if (nk > 0) { drain(2u * GB); tc_fence_before(); }   // the small terms (complete: the last acc_full commit covers every MMA)
   __syncwarp();
   if (lane == 0) mbar_arrive(done);
   compute_barrier();   // every stage converted and every window read: staging / operand memory can be reused as the epilogue tile
