@@ -583,9 +583,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own log (NCCL_DEBUG=INFO / VERSION) goes to stderr unless the caller
-        # already pointed it at a file
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        # stdout carries ONE JSON line: NCCL's own log (NCCL_DEBUG=INFO / VERSION, from the environment or nccl.conf) is
+        # NOT silenced - it goes to stderr unless the caller already pointed it at a file
+        if not os.environ.get("NCCL_DEBUG_FILE"):
             os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 

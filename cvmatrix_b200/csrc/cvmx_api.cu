@@ -232,12 +232,17 @@ std::vector<int64_t> taper_sizes(int64_t n, int64_t R, int levels) {
 
 std::vector<std::vector<int64_t>> plan_tapered(const std::vector<int64_t>& fold_rows, const std::vector<int2>& tiles, int64_t sms,
                                                int64_t r_lo, int64_t r_hi) {
+  // the search costs ~10 ms of host time: remember the last few answers (a refit with the same fold sizes re-plans)
+  struct Memo { std::vector<int64_t> rows; size_t ntiles; int64_t sms; std::vector<std::vector<int64_t>> sizes; };
+  static thread_local std::vector<Memo> memo;
+  for (const Memo& m : memo)
+    if (m.rows == fold_rows && m.ntiles == tiles.size() && m.sms == sms) return m.sizes;
   std::vector<double> tile_cost;
   for (const int2& t : tiles) tile_cost.push_back(t.x == t.y ? 0.78 : 1.0);
   double best = 1e300;
   std::vector<std::vector<int64_t>> best_sizes;
-  for (int64_t R = r_lo; R <= r_hi; R += 4 * GBK)
-    for (int levels = 1; levels <= 4; ++levels) {
+  for (int64_t R = r_lo; R <= r_hi; R += 8 * GBK)
+    for (int levels = 2; levels <= 4; ++levels) {
       std::vector<std::vector<int64_t>> sizes;
       std::vector<int64_t> all;
       for (int64_t n : fold_rows) {
@@ -247,6 +252,8 @@ std::vector<std::vector<int64_t>> plan_tapered(const std::vector<int64_t>& fold_
       const double mk = simulate_makespan(all, tile_cost, sms);
       if (mk < best - 1e-9) { best = mk; best_sizes = sizes; }
     }
+  if (memo.size() >= 8) memo.erase(memo.begin());
+  memo.push_back({fold_rows, tiles.size(), sms, best_sizes});
   return best_sizes;
 }
 
