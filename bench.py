@@ -706,12 +706,28 @@ def main():
 
         parts = {"partitioner_ms": 0.0, "fit_ms": 0.0, "set_folds_ms": 0.0, "folds_ms": 0.0}
 
+        # several GPUs, few huge folds: the e2e path keeps the ROWS sharded (row slabs): every rank uploads only its own
+        # 1 / world of the rows over its PCIe link and nothing is exchanged but the chained column sums (2 ld values per
+        # hop) and the per-slab Grams the fold owners sum over NVLink
+        slab = None
+        if row_sharded and world > 1:
+            from cvmatrix_b200.distributed import RowSlabFolds
+
+            slab = RowSlabFolds(m, N, K, M, w, block_rows=32768)
+            w_pinned = torch.from_numpy(w)
+
         def e2e_step(Xh, Yh, wh, keep_results=False):
             nonlocal out_bytes
             t0 = time.perf_counter()
             p2 = Partitioner(folds)
             t1 = time.perf_counter()
-            if world > 1:
+            if slab is not None:
+                slab.w.copy_(w_pinned, non_blocking=True)                      # the weights are inputs too (8 MB)
+                r0, r1 = slab.row0, slab.row1
+                slab.fit((b0, Xh[b0:min(r1, b0 + 32768)], Yh[b0:min(r1, b0 + 32768)]) for b0 in range(r0, r1, 32768))
+                t2 = time.perf_counter()
+                slab.set_folds(p2)
+            elif world > 1:
                 # every rank uploads 1 / world of the rows over its own PCIe link; slabs are exchanged over NVLink
                 fit_sharded_upload(m, Xh, Yh, wh)
                 t2 = time.perf_counter()
@@ -724,7 +740,7 @@ def main():
             t3 = time.perf_counter()
             out_bytes = 0
             if row_sharded and world > 1:
-                res = sf.training_batch(0, P, out=outs, row_sharded=True)
+                res = slab.training_batch(0, P, out=outs)
                 n = res["fold_end"] - res["fold_begin"]
                 for k, hbuf in host_out.items():
                     if n > 0:
@@ -764,7 +780,7 @@ def main():
             h2d *= world
         e2e = {"value": P / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "includes": ("Partitioner + fit (H2D from pinned host memory" + (f": 1/{world} of the rows per rank, slabs exchanged over NVLink" if world > 1 else "; fused with the fold Grams when the folds partition the rows")
+               "includes": ("Partitioner + fit (H2D from pinned host memory" + ((f": 1/{world} of the rows per rank, rows stay sharded (row slabs: chained column sums, per-slab Grams summed by the fold owners over NVLink)" if slab is not None else f": 1/{world} of the rows per rank, slabs exchanged over NVLink") if world > 1 else "; fused with the fold Grams when the folds partition the rows")
                             + ") + set_folds + all folds + D2H of every output"),
                "host_outputs": args.e2e_out, "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
         if world == 1 and N * K * 8 <= 5e9 and P <= 1000:

@@ -282,6 +282,21 @@ class RowSlabFolds:
         self._step = 0
         self._gram = None
         self.P = 0
+        self._warm_chain()
+
+    def _warm_chain(self) -> None:
+        """One tiny message down the rank chain: NCCL opens its point-to-point channels lazily (~0.2 s per new pair), which
+        would otherwise be paid hop after hop inside the first fit."""
+        if self.world == 1:
+            return
+        t, dist = self.torch, self.dist
+        token = t.zeros(1, dtype=t.float32, device=self.dev)
+        if self.rank > 0:
+            dist.recv(token, src=self._grank(self.rank - 1), group=self.group)
+        if self.rank < self.world - 1:
+            dist.send(token, dst=self._grank(self.rank + 1), group=self.group)
+        dist.broadcast(token, src=self._grank(self.world - 1), group=self.group)
+        t.cuda.current_stream(self.dev).synchronize()
 
     def _grank(self, r: int) -> int:
         return self.dist.get_global_rank(self.group, r) if self.group is not None else r
