@@ -100,6 +100,11 @@ struct cvmx_handle {
   int64_t N_glob = 0, row0 = 0;
   DevBuf w_glob, g_off, g_idx;
   std::vector<int64_t> g_h_off;
+  // decoupled slab chain (cvmx_slab_scan_local / _prepare): which sums the scan planes currently describe
+  int slab_scan_mode = 0;        // 0 none, 1 fit totals, 2 fold sums
+  int slab_scan_stage = 0;       // 1 local passes done, 2 prepared (passes 2 and 3 done)
+  int64_t slab_scan_f0 = 0, slab_scan_f1 = 0, slab_scan_csr = -1;
+  bool fit_pre_done = false;     // fit mode: accumulator -> totals and the weight mass already ran (cvmx_slab_scan_local)
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
   bool filling = false;
   int64_t fill_units_cap = 0, fill_calls = 0;
@@ -464,7 +469,7 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
 
 template <typename T>
 int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard = 0, int n_col_shards = 1,
-                       double overlap_ns = 1e30) {
+                       double overlap_ns = 1e30, const int* done_groups = nullptr, int done_groups_total = 0) {
   if (!h->attr_mom) {
     CU(h, cudaFuncSetAttribute(k_moments_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)moments_pipe_smem<T>(MOM_STAGES_DEEP)));
@@ -486,7 +491,8 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
   // through to k_moments_pipe below.
   bool scan = false;
   const int64_t max_segs = round_up((max_rows + SCAN_L - 1) / SCAN_L, SCAN_PER_LANE);
-  if (std::is_same<T, double>::value && pipe && !mp.ranges && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
+  // done_groups: the binade scan already ran for this call (decoupled slab chain) - only the groups it gave up are left
+  if (std::is_same<T, double>::value && pipe && !mp.ranges && !done_groups && h->scan_mode != 0 && max_rows < ((int64_t)1 << 25)) {
     const size_t seg_bytes = (size_t)std::min<int64_t>(65535, nfolds) * max_segs * 4 * mp.ld * sizeof(double);
     const int64_t groups0 = mp.ld / MOM_COLS;
     const int64_t mine0 = groups0 > col_shard ? (groups0 - col_shard + n_col_shards - 1) / n_col_shards : 0;
@@ -510,6 +516,7 @@ int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t ma
       q.raw = mp.raw ? mp.raw + (size_t)f0 * 2 * mp.ld : nullptr;
     }
     q.grp0 = col_shard; q.grp_stride = n_col_shards;
+    if (done_groups) { q.scan_ok = done_groups + f0 * done_groups_total; q.scan_groups = done_groups_total; }
     const int64_t groups = pipe ? mp.ld / MOM_COLS : (mp.ld + 127) / 128;
     const int64_t mine = groups > col_shard ? (groups - col_shard + n_col_shards - 1) / n_col_shards : 0;
     if (mine == 0) continue;
@@ -1077,23 +1084,103 @@ int32_t fit_rows_impl(cvmx_t* h, int64_t row0, int64_t nr, const void* X, int64_
   return CVMX_OK;
 }
 
-struct SlabArgs { const void* carry_sum; const void* carry_sumsq; const void* w_glob; int64_t N_glob; int64_t row0; };
+// ---- decoupled slab chain (row-slab mode, float64) --------------------------------------------------------------------
+// numpy's column sums are sequential over ALL rows, so rank r can only finish its slab's chains once rank r - 1 has.  Only
+// pass 4 of the binade scan needs the exact incoming value, though: passes 1 - 3 need the running sum at the slab's first
+// row only APPROXIMATELY (to classify segments by binade, inside pass 2's usual error margin), and that is the sum of the
+// earlier slabs' pass-1 totals - a row of 4 ld values per slab that the ranks all-gather.  Every rank then runs passes
+// 1 - 3 at once and a hop of the rank-to-rank chain costs one short kernel (one exact addition per 256 rows).
+//   mode 1: all rows of the slab (fit totals, chains in sum_z / sumsq_z)      mode 2: folds [f0, f1) of the local CSR
+int32_t slab_scan_params(cvmx_t* h, int mode, int64_t f0, int64_t f1, ScanParams& sp, int64_t& Pn, int64_t& max_rows, bool& applicable) {
+  const int64_t ld = h->ld;
+  Pn = mode == 1 ? 1 : f1 - f0;
+  max_rows = 0;
+  if (mode == 1) max_rows = h->N;
+  else for (int64_t f = f0; f < f1; ++f) max_rows = std::max(max_rows, h->h_off[f + 1] - h->h_off[f]);
+  const int64_t max_segs = round_up((max_rows + SCAN_L - 1) / SCAN_L, SCAN_PER_LANE);
+  const int64_t groups = ld / MOM_COLS;
+  const size_t seg_bytes = (size_t)Pn * max_segs * 4 * ld * sizeof(double);
+  applicable = h->dtype == CVMX_F64 && h->scan_mode != 0 && Pn <= 65535 && max_rows >= 4 * SCAN_L && max_rows < ((int64_t)1 << 25) &&
+               seg_bytes <= ((size_t)2 << 30);
+  if (!applicable) return CVMX_OK;
+  MomentParams<double> mp;
+  mp.Z = h->Z.as<double>(); mp.w = h->w.as<double>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
+  mp.N = h->N; mp.flags = h->flags; mp.resolution = h->resolution;
+  mp.sum_z = h->sum_z.as<double>(); mp.sumsq_z = h->sumsq_z.as<double>();
+  mp.fs = nullptr; mp.pw_cols = nullptr; mp.stats = nullptr;
+  if (mode == 2) { mp.offsets = h->d_off.as<int64_t>(); mp.indices = h->d_idx.as<int64_t>(); mp.fold0 = f0; }
+  else { mp.offsets = nullptr; mp.indices = nullptr; mp.fold0 = 0; mp.pw_cols = h->pwcols.as<double>(); }
+  mp.grp0 = 0; mp.grp_stride = 1;
+  sp.p = mp; sp.L = SCAN_L; sp.max_segs = max_segs; sp.groups_total = (int)groups;
+  sp.slow_cap = (int)(max_segs / 4 + 2);
+  CU(h, h->scan_seg.reserve(seg_bytes));
+  CU(h, h->scan_ok.reserve((size_t)Pn * groups * sizeof(int)));
+  CU(h, h->scan_list.reserve((size_t)Pn * 2 * sp.slow_cap * ld * sizeof(int)));
+  CU(h, h->scan_cnt.reserve((size_t)Pn * 2 * ld * sizeof(int)));
+  sp.seg = h->scan_seg.as<double>(); sp.ok = h->scan_ok.as<int>();
+  sp.slow_list = h->scan_list.as<int>(); sp.slow_cnt = h->scan_cnt.as<int>();
+  return CVMX_OK;
+}
+
+inline dim3 slab_scan_grid(const ScanParams& sp, int64_t Pn) {
+  return dim3((unsigned)sp.groups_total, (unsigned)((sp.max_segs + SCAN_WARPS - 1) / SCAN_WARPS), (unsigned)Pn);
+}
+
+// passes 1 and 1b: tot_out [Pn][2][2][ld] (device) = this slab's approximate sums and sums of magnitudes
+int32_t slab_scan_local(cvmx_t* h, int mode, int64_t f0, int64_t f1, double* tot_out, bool& applicable) {
+  ScanParams sp; int64_t Pn, max_rows;
+  int32_t rc = slab_scan_params(h, mode, f0, f1, sp, Pn, max_rows, applicable);
+  if (rc || !applicable) return rc;
+  k_scan_segsums<<<slab_scan_grid(sp, Pn), 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+  k_scan_slab_totals<<<dim3((unsigned)((h->ld + 3) / 4), (unsigned)Pn), 128, 0, h->stream>>>(sp, tot_out);
+  h->launches += 2; h->scan_launches += 1;
+  CU(h, cudaGetLastError());
+  h->slab_scan_mode = mode; h->slab_scan_stage = 1; h->slab_scan_f0 = f0; h->slab_scan_f1 = f1; h->slab_scan_csr = h->csr_version;
+  return CVMX_OK;
+}
+
+// passes 2 and 3 from the approximate start [Pn][2][2][ld] (device): sums of the earlier slabs' tot_out rows
+int32_t slab_scan_prepare(cvmx_t* h, int mode, int64_t f0, int64_t f1, const double* start) {
+  ScanParams sp; int64_t Pn, max_rows; bool applicable;
+  int32_t rc = slab_scan_params(h, mode, f0, f1, sp, Pn, max_rows, applicable);
+  if (rc) return rc;
+  if (!applicable) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_prepare: cvmx_slab_scan_local reported the scan not applicable");
+  sp.start = start;
+  k_scan_prefix<false><<<dim3((unsigned)(sp.groups_total * SCAN_PREFIX_CTAS), (unsigned)Pn), SCAN_PREFIX_THREADS, 0, h->stream>>>(sp, nullptr);
+  k_scan_delta<<<slab_scan_grid(sp, Pn), 32 * SCAN_WARPS, 0, h->stream>>>(sp);
+  h->launches += 2;
+  CU(h, cudaGetLastError());
+  h->slab_scan_stage = 2;
+  return CVMX_OK;
+}
 
 template <typename T>
-int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const SlabArgs* sl = nullptr) {
-  const int64_t N = h->N, K = h->K, M = h->M, ld = h->ld;
-  if (sl) {
-    // row-slab mode: the weight sums need every weight of the data set, the moment chains continue the previous slab's
-    if (h->weighted) {
-      CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(sl->N_glob, 1) * sizeof(T)));
-      CU(h, cudaMemcpyAsync(h->w_glob.p, sl->w_glob, (size_t)sl->N_glob * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-    }
-    if (sl->carry_sum) {
-      CU(h, cudaMemcpyAsync(h->sum_z.p, sl->carry_sum, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-      CU(h, cudaMemcpyAsync(h->sumsq_z.p, sl->carry_sumsq, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
-    }
-    h->slab = true; h->N_glob = sl->N_glob; h->row0 = sl->row0;
-  }
+int32_t launch_moments(cvmx_t* h, MomentParams<T> mp, int64_t nfolds, int64_t max_rows, int col_shard, int n_col_shards,
+                       double overlap_ns, const int* done_groups, int done_groups_total);
+
+// pass 4 from the exact chains of the previous slab: carry [Pn][2][ld] (fold mode, in / out) or sum_z / sumsq_z (fit mode,
+// chain_mp.accumulate says whether they hold a previous slab's values); groups the scan gave up run the chain kernel
+// (chain_mp: the MomentParams the undecoupled path would have launched)
+int32_t slab_scan_finish(cvmx_t* h, int mode, int64_t f0, int64_t f1, double* carry, const MomentParams<double>& chain_mp) {
+  ScanParams sp; int64_t Pn, max_rows; bool applicable;
+  int32_t rc = slab_scan_params(h, mode, f0, f1, sp, Pn, max_rows, applicable);
+  if (rc) return rc;
+  if (!applicable) return fail(h, CVMX_ERR_INVALID, "decoupled slab chain: not prepared");
+  sp.p.accumulate = chain_mp.accumulate;
+  if (mode == 2) { sp.carry = carry; sp.p.raw = carry; }
+  k_scan_chain<2><<<dim3((unsigned)(sp.groups_total * (SCAN_COLS / 2)), (unsigned)Pn), 64 * 2, scan_chain_smem<2>(), h->stream>>>(sp);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return launch_moments<double>(h, chain_mp, Pn, max_rows, 0, 1, 0.0, sp.ok, sp.groups_total);
+}
+
+struct SlabArgs { const void* carry_sum; const void* carry_sumsq; const void* w_glob; int64_t N_glob; int64_t row0; };
+
+// The part of cvmx_fit_end that does not depend on the moment chains: accumulator -> totals, weight mass.
+// use_w_glob: the weight mass runs over h->w_glob (row slabs: all N_w weights of the data set).
+template <typename T>
+int32_t fit_end_pre(cvmx_t* h, bool use_w_glob, int64_t N_w) {
+  const int64_t K = h->K, M = h->M, ld = h->ld;
   // accumulator -> totals (raw epilogue: mirrored XtWX, XtWY)
   std::vector<int2> tiles;
   plan_tiles(h, (uint32_t)(CVMX_WANT_XTX | (M > 0 ? CVMX_WANT_XTY : 0)), tiles);
@@ -1116,10 +1203,31 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
   h->launches++;
   CU(h, cudaGetLastError());
   // statistics over all rows: weight mass everywhere, moment sums for this column shard (others stay zero)
-  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), sl && h->weighted ? h->w_glob.as<T>() : h->w.as<T>(), ld,
-                                                                          sl ? sl->N_glob : N, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), use_w_glob && h->weighted ? h->w_glob.as<T>() : h->w.as<T>(), ld,
+                                                                          N_w, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
                                                                           h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
   h->launches++;
+  CU(h, cudaGetLastError());
+  return CVMX_OK;
+}
+
+template <typename T>
+int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const SlabArgs* sl = nullptr) {
+  const int64_t N = h->N, K = h->K, M = h->M, ld = h->ld;
+  if (sl) {
+    // row-slab mode: the weight sums need every weight of the data set, the moment chains continue the previous slab's
+    if (h->weighted && !h->fit_pre_done) {
+      CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(sl->N_glob, 1) * sizeof(T)));
+      CU(h, cudaMemcpyAsync(h->w_glob.p, sl->w_glob, (size_t)sl->N_glob * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (sl->carry_sum) {
+      CU(h, cudaMemcpyAsync(h->sum_z.p, sl->carry_sum, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+      CU(h, cudaMemcpyAsync(h->sumsq_z.p, sl->carry_sumsq, ld * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->slab = true; h->N_glob = sl->N_glob; h->row0 = sl->row0;
+  }
+  if (!h->fit_pre_done) { int32_t rp = fit_end_pre<T>(h, sl != nullptr, sl ? sl->N_glob : N); if (rp) return rp; }
+  h->fit_pre_done = false;
   MomentParams<T> mp;
   mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = K; mp.M = M;
   mp.offsets = nullptr; mp.indices = nullptr; mp.fold0 = 0; mp.N = N;
@@ -1127,7 +1235,15 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
   mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
   mp.fs = nullptr; mp.pw_cols = h->pwcols.as<T>(); mp.stats = nullptr;
   mp.accumulate = (sl && sl->carry_sum) ? 1 : 0;
-  int32_t rc = launch_moments<T>(h, mp, 1, N, col_shard, n_col_shards, 0.0);
+  int32_t rc;
+  if (sl && h->slab_scan_mode == 1 && h->slab_scan_stage == 2) {
+    // the scan passes that do not need the previous slab's chains already ran (cvmx_slab_scan_local / _prepare)
+    if constexpr (std::is_same<T, double>::value) rc = slab_scan_finish(h, 1, 0, 1, nullptr, mp);
+    else rc = fail(h, CVMX_ERR_INVALID, "decoupled slab chain: float64 only");
+  } else {
+    rc = launch_moments<T>(h, mp, 1, N, col_shard, n_col_shards, 0.0);
+  }
+  h->slab_scan_mode = 0; h->slab_scan_stage = 0;
   if (rc) return rc;
   FitScalars fsc;
   CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
@@ -1519,7 +1635,16 @@ int32_t slab_fold_sums(cvmx_t* h, int64_t f0, int64_t f1, void* carry) {
   fc.fs = nullptr; fc.pw_cols = nullptr; fc.stats = nullptr;
   fc.ranges = h->chunk_ranges.as<int64_t>(); fc.raw = (T*)carry; fc.accumulate = 1;
   const int ev0 = prof_mark(h);
-  int32_t rc = launch_moments<T>(h, fc, Pn, max_rows);
+  int32_t rc;
+  const bool prepared = h->slab_scan_mode == 2 && h->slab_scan_stage == 2 && h->slab_scan_f0 == f0 && h->slab_scan_f1 == f1 &&
+                        h->slab_scan_csr == h->csr_version;
+  if (prepared) {
+    if constexpr (std::is_same<T, double>::value) rc = slab_scan_finish(h, 2, f0, f1, (double*)carry, fc);
+    else rc = fail(h, CVMX_ERR_INVALID, "decoupled slab chain: float64 only");
+  } else {
+    rc = launch_moments<T>(h, fc, Pn, max_rows);
+  }
+  h->slab_scan_mode = 0; h->slab_scan_stage = 0;
   prof_span(h, PROF_STATS, ev0, prof_mark(h));
   return rc;
 }
@@ -1905,6 +2030,50 @@ int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_su
   ON_DEVICE(h);
   SlabArgs sl{carry_sum, carry_sumsq, w_glob, N_glob, row0};
   return h->dtype == CVMX_F64 ? fit_end_impl<double>(h, 0, 1, &sl) : fit_end_impl<float>(h, 0, 1, &sl);
+}
+
+int32_t cvmx_slab_scan_local(cvmx_t* h, int64_t f0, int64_t f1, const void* w_glob, int64_t N_glob, int64_t row0, double* tot_out,
+                             int32_t* applicable) {
+  if (!h || !tot_out || !applicable) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: null argument");
+  *applicable = 0;
+  const bool fit_mode = f0 < 0;
+  if (fit_mode) {
+    if (!h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: fit totals need cvmx_fit_begin / cvmx_fit_rows first");
+    if (N_glob < h->N || row0 < 0 || row0 + h->N > N_glob || (h->weighted && !w_glob)) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: bad slab arguments");
+    if (h->K < 2 || h->M == 1) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: row slabs need K >= 2 and M != 1");
+  } else {
+    if (!h->fitted || !h->slab) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: fit a row slab first (cvmx_fit_end_slab)");
+    if (f1 > h->P || f0 >= f1) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: bad fold range");
+  }
+  if (h->dtype != CVMX_F64) return CVMX_OK;   // float32 chains have no scan: the caller keeps the serial hand-over
+  ON_DEVICE(h);
+  bool app = false;
+  if (fit_mode) {
+    // everything of cvmx_fit_end_slab that does not depend on the previous slab: global weights, accumulator -> totals, weight mass
+    if (h->weighted) {
+      CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(N_glob, 1) * sizeof(double)));
+      CU(h, cudaMemcpyAsync(h->w_glob.p, w_glob, (size_t)N_glob * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->slab = true; h->N_glob = N_glob; h->row0 = row0;
+    int32_t rp = fit_end_pre<double>(h, true, N_glob);
+    if (rp) return rp;
+    h->fit_pre_done = true;
+  }
+  int32_t rc = slab_scan_local(h, fit_mode ? 1 : 2, fit_mode ? 0 : f0, fit_mode ? 1 : f1, tot_out, app);
+  *applicable = app ? 1 : 0;
+  return rc;
+}
+
+int32_t cvmx_slab_scan_prepare(cvmx_t* h, int64_t f0, int64_t f1, const double* start) {
+  if (!h || !start) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_prepare: null argument");
+  const bool fit_mode = f0 < 0;
+  const int mode = fit_mode ? 1 : 2;
+  if (fit_mode) { f0 = 0; f1 = 1; }
+  if (h->slab_scan_mode != mode || h->slab_scan_stage != 1 || h->slab_scan_f0 != f0 || h->slab_scan_f1 != f1 ||
+      (mode == 2 && h->slab_scan_csr != h->csr_version))
+    return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_prepare: call cvmx_slab_scan_local for the same sums first");
+  ON_DEVICE(h);
+  return slab_scan_prepare(h, mode, f0, f1, start);
 }
 
 int32_t cvmx_set_weight_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P) {

@@ -15,7 +15,7 @@ namespace cvmx {
 
 constexpr int GB = 128;       // tile edge (output rows and columns per CTA)
 constexpr int GBK = 16;       // data rows (reduction index) per pipeline stage
-constexpr int GSTAGES = 4;    // cp.async ring depth
+constexpr int GSTAGES = 4;    // ring depth of the row pipeline (6 stages measured: 1 % slower at cfg 2 / cfg 3)
 constexpr int GTHREADS = 256; // 8 warps = 2 (rows) x 4 (cols), warp tile 64 x 32
 constexpr int GACC = 64;      // accumulator doubles per thread
 constexpr int GTILE_ELEMS = GB * GB;
@@ -85,9 +85,33 @@ struct GramParams {
 template <typename T>
 __host__ __device__ constexpr size_t gram_smem_bytes() {
   size_t pipe = sizeof(T) * ((size_t)2 * GSTAGES * GBK * GramCfg<T>::PITCH + (size_t)GSTAGES * GBK);
-  size_t stage = sizeof(T) * (size_t)GB * GramCfg<T>::CPITCH;
+  size_t stage = sizeof(T) * (size_t)GB * GramCfg<T>::CPITCH + 2 * GB * sizeof(double);   // staged tile + reciprocal std rows
   size_t body = (pipe > stage ? pipe : stage);
   return (body + 15) / 16 * 16 + 2 * GSTAGES * sizeof(uint64_t);   // + full / empty mbarriers at the end
+}
+
+// Scaling step of the epilogue.  numpy divides every element by (s_i * s_j); here the reciprocals r = 1 / s are formed
+// once per tile row / column (float64 for both model dtypes) and an element costs two multiplications,
+//   A_ij = rn_T(A_ij * (r_i * r_j)),
+// within ~3 ulp of the quotient - matrices owe the reference 1e-12 (1e-5), only the statistics owe it their bits.  The
+// IEEE division it replaces is ~25 dependent FP64 instructions per element on the pipe the DMMAs saturate.
+template <typename T>
+__device__ __forceinline__ T gram_scale(T a, double ri, double rj) { return (T)__dmul_rn((double)a, __dmul_rn(ri, rj)); }
+
+// rrow[r] (r < nrows: tile rows i0 + r, always X columns) and rcol[c] (c < GB: tile columns j0 + c, X or Y) for the
+// calling thread group (t = thread index inside the group of nthr threads)
+template <typename T>
+__device__ __forceinline__ void gram_recip_rows(const EpiParams<T>& e, const T* __restrict__ sdev, int64_t i0, int64_t j0, int t, int nthr,
+                                                int nrows, double* rrow, double* rcol) {
+  const bool sX = e.flags & 4, sY = e.flags & 8;
+  const int64_t K = e.K, C = e.K + e.M;
+  for (int x = t; x < nrows + GB; x += nthr) {
+    const bool row = x < nrows;
+    const int64_t col = row ? i0 + x : j0 + (x - nrows);
+    const bool on = col < C && (col < K ? sX : sY) && !(row && col >= K);
+    const double r = on ? __ddiv_rn(1.0, (double)sdev[col]) : 1.0;
+    if (row) rrow[x] = r; else rcol[x - nrows] = r;
+  }
 }
 
 // Epilogue of one 128 x 128 tile.
@@ -98,7 +122,7 @@ __host__ __device__ constexpr size_t gram_smem_bytes() {
 //          (each op individually rounded; cvmatrix/cvmatrix.py:1001-1009).  Diagonal tiles skip the lower half.
 //  pass 3  coalesced stores: the tile itself (a diagonal tile takes its lower half from the upper half, so the
 //          result is exactly symmetric) and, for off-diagonal tiles, the mirrored XTX block.
-template <typename T>
+template <typename T, int U = 16>
 __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, const EpiParams<T>& e, int fold, int bi,
                                               int bj, int fmap = 0) {
   constexpr int CP = GramCfg<T>::CPITCH;
@@ -135,12 +159,16 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
       }
     }
   }
+  // reciprocal standard deviations of the tile's rows and columns, behind the staged tile (gram_smem_bytes reserves them)
+  double* rrow = reinterpret_cast<double*>(sC + (size_t)GB * CP);
+  double* rcol = rrow + GB;
+  if (e.mode == 1 && (e.flags & 12))
+    gram_recip_rows<T>(e, e.stats + (size_t)fold * 2 * ld + ld, (int64_t)bi * GB, (int64_t)bj * GB, tid, GTHREADS, GB, rrow, rcol);
   compute_barrier();
 
   if (e.mode == 1) {
     const bool cX = e.flags & 1, cY = e.flags & 2, sX = e.flags & 4, sY = e.flags & 8;
     const T* __restrict__ mean = e.stats + (size_t)fold * 2 * ld;
-    const T* __restrict__ sdev = mean + ld;
     const T* __restrict__ Tt = e.Ttot;
     const T sw = (T)e.fs[fold].sw;
     // thread -> fixed column pair c, rows r0, r0 + 4, ...: the column statistics are loaded once, and the loads of
@@ -149,14 +177,15 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
     const int64_t j = (int64_t)bj * GB + c;
     if (j < C) {
       const vec2 mj = *reinterpret_cast<const vec2*>(mean + j);
-      const vec2 sj = *reinterpret_cast<const vec2*>(sdev + j);
-      const T mjj[2] = {mj.x, mj.y}, sjj[2] = {sj.x, sj.y};
+      const T mjj[2] = {mj.x, mj.y};
+      const double rjj[2] = {rcol[c], rcol[c + 1]};
       const bool isX[2] = {j < K, j + 1 < K};
-      constexpr int U = 4;
+      // U rows per batch: the accumulators are dead here, so 16 loads of the totals tile fly together (2 L2 round trips
+      // per tile instead of 8; k_gram_tc has no setmaxnreg split and keeps 4)
 #pragma unroll 1
       for (int it0 = 0; it0 < GB / 4; it0 += U) {
         vec2 tv[U];
-        T mi[U], si[U];
+        T mi[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -166,7 +195,6 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
           if (ok[u]) {
             tv[u] = __ldg(reinterpret_cast<const vec2*>(Tt + i * ld + j));
             mi[u] = __ldg(mean + i);
-            si[u] = __ldg(sdev + i);
           }
         }
 #pragma unroll
@@ -175,17 +203,11 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
           const int r = r0 + 4 * (it0 + u);
           vec2 gv = *reinterpret_cast<const vec2*>(sC + r * CP + c);
           T a[2] = {Rn<T>::sub(tv[u].x, gv.x), Rn<T>::sub(tv[u].y, gv.y)};
+          const double ri_u = rrow[r];
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            if (isX[x]) {
-              if (cX) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi[u], mjj[x])));
-              if (sX) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si[u], sjj[x]));
-            } else {
-              if (cX || cY) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi[u], mjj[x])));
-              if (sX && sY) a[x] = Rn<T>::div(a[x], Rn<T>::mul(si[u], sjj[x]));
-              else if (sX) a[x] = Rn<T>::div(a[x], si[u]);
-              else if (sY) a[x] = Rn<T>::div(a[x], sjj[x]);
-            }
+            if (isX[x] ? cX : (cX || cY)) a[x] = Rn<T>::sub(a[x], Rn<T>::mul(sw, Rn<T>::mul(mi[u], mjj[x])));
+            if (sX || sY) a[x] = gram_scale<T>(a[x], ri_u, rjj[x]);
           }
           gv.x = a[0]; gv.y = a[1];
           *reinterpret_cast<vec2*>(sC + r * CP + c) = gv;

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram_tc(const GramParams<float> 
   compute_barrier();   // every stage converted and every window read: staging / operand memory can be reused as the epilogue tile
 
   if (unit.nsplit == 1 && !p.force_partials) {
-    gram_epilogue<float>(acc, reinterpret_cast<float*>(smem), p.epi, unit.fold, bi, bj, 1);
+    gram_epilogue<float, 4>(acc, reinterpret_cast<float*>(smem), p.epi, unit.fold, bi, bj, 1);
   } else {
     double* dst = p.partials + ((size_t)(unit.part_base + unit.split) * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
 #pragma unroll

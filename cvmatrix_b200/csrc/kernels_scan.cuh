@@ -48,6 +48,12 @@ struct ScanParams {
   int L;
   int64_t max_segs;
   int groups_total;
+  // row-slab mode, decoupled chain (cvmx_slab_scan_*): the rows before this slab live on other ranks.
+  //   start [folds][chain][2: prefix, magnitudes][ld]: APPROXIMATE running sum and sum of magnitudes at the slab's first row
+  //         (any summation order - pass 2 only classifies segments with them, inside its usual error margin)
+  //   carry [folds][chain][ld]: the EXACT chains after the previous slab - pass 4 continues them
+  const double* start = nullptr;
+  const double* carry = nullptr;
 };
 
 // element (segment s, column c) of plane (fold f, chain, slot)
@@ -126,6 +132,33 @@ __global__ void __launch_bounds__(32 * SCAN_WARPS) k_scan_segsums(ScanParams sp)
   }
 }
 
+// ---- pass 1b (row slabs) ----------------------------------------------------------------------------------------------
+// Slab totals of the pass-1 planes: out[fold][chain][0] = sum of S, [1] = sum of A over the slab's segments, per column.
+// The ranks exchange these (tiny) rows; the totals of the slabs before a rank are its `start`.  One warp per column.
+__global__ void __launch_bounds__(128) k_scan_slab_totals(ScanParams sp, double* __restrict__ out) {
+  const MomentParams<double>& p = sp.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t f = blockIdx.y;
+  const int64_t c = (int64_t)blockIdx.x * 4 + warp;
+  if (c >= p.ld) return;
+  const int64_t beg = p.offsets ? p.offsets[p.fold0 + f] : 0;
+  const int64_t n = p.offsets ? p.offsets[p.fold0 + f + 1] - beg : p.N;
+  const int64_t nseg = (n + sp.L - 1) / sp.L;
+  for (int chain = 0; chain < 2; ++chain) {
+    const double* dS = scan_plane(sp, f, chain, 0, c);
+    const double* dA = scan_plane(sp, f, chain, 1, c);
+    double S = 0.0, A = 0.0;
+    if (c < p.K + p.M)
+      for (int64_t s = lane; s < nseg; s += 32) { S += dS[s]; A += dA[s]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); A += __shfl_xor_sync(0xffffffffu, A, o); }
+    if (lane == 0) {
+      out[(((size_t)f * 2 + chain) * 2 + 0) * p.ld + c] = S;
+      out[(((size_t)f * 2 + chain) * 2 + 1) * p.ld + c] = A;
+    }
+  }
+}
+
 // ---- pass 2 -----------------------------------------------------------------------------------------------------
 // SCAN_PREFIX_CTAS CTAs per (column group, fold), one warp per column.  256 segments per trip: every lane owns 8 consecutive
 // segments (16 independent loads in flight), prefixes them locally, and a warp scan supplies the lane offsets (the
@@ -151,7 +184,10 @@ __global__ void __launch_bounds__(SCAN_PREFIX_THREADS) k_scan_prefix(ScanParams 
   if (c < p.K + p.M) {
     for (int chain = 0; chain < 2; ++chain) {
       double P = 0.0, tot = 0.0;
-      if (p.accumulate) P = chain == 0 ? p.sum_z[c] : p.sumsq_z[c];
+      if (sp.start) {
+        P = sp.start[(((size_t)f * 2 + chain) * 2 + 0) * p.ld + c];
+        tot = sp.start[(((size_t)f * 2 + chain) * 2 + 1) * p.ld + c];
+      } else if (p.accumulate) P = chain == 0 ? p.sum_z[c] : p.sumsq_z[c];
       double* dS = scan_plane(sp, f, chain, 0, c);
       double* dA = scan_plane(sp, f, chain, 1, c);
       const double* gB = SPEC ? scan_spec_plane(sp, const_cast<double*>(spec), f, chain, 0, c) : nullptr;
@@ -306,7 +342,8 @@ __global__ void __launch_bounds__(64 * SCAN_CHAIN_COLS) k_scan_chain(ScanParams 
   double2* sd = reinterpret_cast<double2*>(sv + SCAN_L);                               // [32] (d0, d1) of the current trip
   double acc = 0.0;
   if (c < p.K + p.M) {
-    if (p.accumulate) acc = chain == 0 ? p.sum_z[c] : p.sumsq_z[c];
+    if (sp.carry) acc = sp.carry[((size_t)f * 2 + chain) * p.ld + c];
+    else if (p.accumulate) acc = chain == 0 ? p.sum_z[c] : p.sumsq_z[c];
     const double* d0p = scan_plane(sp, f, chain, 0, c);
     const double* d1p = scan_plane(sp, f, chain, 1, c);
     const double* zc = p.Z + c;

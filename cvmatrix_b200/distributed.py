@@ -278,6 +278,9 @@ class RowSlabFolds:
             weights = torch.from_numpy(self.w_host).to(self.dev)
         self.w = weights                     # all N weights, on the device (None: unweighted)
         self.use_peers = self.world > 1 and self.world <= 8 and self.f64
+        import os
+
+        self.decouple = os.environ.get("CVMX_SLAB_DECOUPLE", "1") != "0"   # scan passes before the carry arrives (float64)
         self._symm = None
         self._step = 0
         self._gram = None
@@ -320,11 +323,13 @@ class RowSlabFolds:
                     wb = self.w_host[b0:b0 + nb]
             cvm.fit_rows(b0 - self.row0, Xb, Yb if self.M else None, wb, gram=True)
         ld = int(lib.cvmx_ld(h))
+        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
+        # decoupled chain: every rank runs the streaming scan passes of its slab now; only the last pass waits for the carry
+        self._decoupled(-1, 0, 1, ld, w_args=(vp(self.w), self.N, self.row0))
         carry = t.zeros((2, ld), dtype=self.tdt, device=self.dev)
         if self.world > 1 and self.rank > 0:
             dist.recv(carry, src=self._grank(self.rank - 1), group=self.group)
             t.cuda.current_stream(self.dev).synchronize()
-        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
         first = self.rank == 0
         _lib.check(lib.cvmx_fit_end_slab(h, None if first else vp(carry[0]), None if first else vp(carry[1]), vp(self.w), self.N, self.row0), h)
         sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
@@ -348,6 +353,29 @@ class RowSlabFolds:
         cvm._streamed = True
         cvm.N = self.N
         cvm._pull_totals()
+
+    def _decoupled(self, f0: int, f1: int, n_sets: int, ld: int, w_args=(None, 0, 0)) -> bool:
+        """Streaming passes of the binade scan for the fit totals (f0 < 0) or the folds [f0, f1) of this slab, before the
+        previous slab's chains are known (include/cvmx.h, "Decoupled slab chain"): local totals -> all-gather -> sums of the
+        earlier slabs = approximate start -> passes 2 and 3.  Returns False (nothing done, on every rank) when some rank
+        cannot take the path (float32, a slab too short); the chained call that follows then does all the work itself."""
+        if self.world == 1 or not self.f64 or not self.decouple:
+            return False
+        t, dist, cvm = self.torch, self.dist, self.cvm
+        lib, h = cvm._lib, cvm._h
+        n = n_sets * 4 * ld
+        mine = t.zeros((n + 1,), dtype=t.float64, device=self.dev)
+        app = C.c_int32(0)
+        _lib.check(lib.cvmx_slab_scan_local(h, f0, f1, w_args[0], w_args[1], w_args[2], C.c_void_p(mine.data_ptr()), C.byref(app)), h)
+        mine[n] = float(app.value)
+        allv = t.empty((self.world, n + 1), dtype=t.float64, device=self.dev)
+        dist.all_gather_into_tensor(allv, mine, group=self.group)
+        if float(allv[:, n].min().item()) < 1.0:          # one host sync per call; every rank sees the same flags
+            return False                                   # the planes of a local-only attempt are never used
+        start = allv[:self.rank, :n].sum(dim=0) if self.rank > 0 else t.zeros((n,), dtype=t.float64, device=self.dev)
+        _lib.check(lib.cvmx_slab_scan_prepare(h, f0, f1, C.c_void_p(start.data_ptr())), h)
+        self._start_keepalive = start     # the kernels read it asynchronously
+        return True
 
     def set_folds(self, folds) -> None:
         from .partitioner import Partitioner
@@ -391,7 +419,8 @@ class RowSlabFolds:
         vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
         want = _lib.WANT_XTX | (_lib.WANT_XTY if self.M else 0)
         ld = int(lib.cvmx_ld(h))
-        # 1. the folds' column sums, chained slab to slab in row order
+        # 1. the folds' column sums, chained slab to slab in row order (streaming scan passes first, on every rank at once)
+        self._decoupled(f0, f1, f1 - f0, ld)
         carry = t.zeros((f1 - f0, 2, ld), dtype=self.tdt, device=self.dev)
         if self.world > 1 and self.rank > 0:
             dist.recv(carry, src=self._grank(self.rank - 1), group=self.group)

@@ -236,6 +236,23 @@ int32_t cvmx_sharded_finish_peers(cvmx_t* h, int64_t batch_f0, int64_t batch_f1,
  *                              (called with gram_count < 0: no statistics rows to sum).
  */
 int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_sumsq, const void* w_glob, int64_t N_glob, int64_t row0);
+
+/* Decoupled slab chain (float64).  The chained column sums above make rank r wait for rank r - 1, but only the LAST pass of
+ * the binade scan (kernels_scan.cuh: one exact addition per 256 rows) needs the exact incoming chains; the streaming
+ * passes need the running sum at the slab's first row only approximately - and that is the sum of the earlier slabs'
+ * approximate totals, which the ranks all-gather (4 ld values per slab and fold).  The same numpy sums are replaced
+ * (cvmatrix/cvmatrix.py:1231-1241 fit, :709-737 folds); results stay bit-identical to the sequential chain.
+ *   cvmx_slab_scan_local   : f0 < 0: the fit totals of this slab, after the last cvmx_fit_rows (w_glob / N_glob / row0 as
+ *                            for cvmx_fit_end_slab, which must follow with the same values; also runs everything of it
+ *                            that does not depend on the previous slab).  f0 >= 0: folds [f0, f1) of the local CSR.
+ *                            tot_out [folds][2 chains][2][ld] float64 (device): this slab's approximate sums and sums of
+ *                            magnitudes.  *applicable = 0: slab too small / float32 - nothing was done, use the plain
+ *                            chained calls.  Every rank must take the same path (all-reduce the flag).
+ *   cvmx_slab_scan_prepare : start = the sum of tot_out over all EARLIER slabs (zeros on the first), same layout.
+ *   then cvmx_fit_end_slab / cvmx_slab_fold_sums with the exact carry as before: they run only the last pass. */
+int32_t cvmx_slab_scan_local(cvmx_t* h, int64_t f0, int64_t f1, const void* w_glob, int64_t N_glob, int64_t row0, double* tot_out,
+                             int32_t* applicable);
+int32_t cvmx_slab_scan_prepare(cvmx_t* h, int64_t f0, int64_t f1, const double* start);
 int32_t cvmx_set_weight_folds(cvmx_t* h, const int64_t* offsets, const int64_t* indices, int64_t P);
 int32_t cvmx_slab_fold_sums(cvmx_t* h, int64_t f0, int64_t f1, void* carry);
 int32_t cvmx_slab_finalize_stats(cvmx_t* h, int64_t f0, int64_t f1, const void* raw);

@@ -148,3 +148,118 @@ def test_two_slabs_on_one_device_chain_by_hand():
         st = ost[pos].cpu().numpy()
         assert np.array_equal(st[0, :K], r.X_mean[0]) and np.array_equal(st[1, :K], r.X_std[0])
         assert np.array_equal(st[0, K:], r.Y_mean[0]) and np.array_equal(st[1, K:], r.Y_std[0])
+
+
+def test_three_slabs_decoupled_chain_by_hand():
+    """The decoupled slab chain (cvmx_slab_scan_local / _prepare): every slab runs the streaming scan passes from an
+    APPROXIMATE start (the sum of the earlier slabs' pass-1 totals) before the exact chains arrive; only the last pass is
+    chained.  Sums and statistics must still be bit-identical to numpy's sequential sums over all rows."""
+    import torch
+
+    from cvmatrix_b200 import CVMatrix, Partitioner, _lib, sharding
+    from cvmatrix_b200.distributed import _DevArray
+
+    X, Y, w, labels = _inputs(N=30_000, seed=23)
+    X[:, 3] -= 0.5            # a column whose running sum wanders around zero: segments the scan must hand to the chain kernel
+    N, K = X.shape
+    M = Y.shape[1]
+    part = Partitioner(labels)
+    offsets, indices = part.csr()
+    P = offsets.size - 1
+    orc = OracleCVMatrix()
+    orc.fit(X, Y, w)
+    dev = torch.device("cuda", 0)
+    wg = torch.from_numpy(w).to(dev)
+    vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+    world = 3
+    hs, slabs, tots = [], [], []
+    # ---- fit, phase 1 on every slab: rows in, local scan passes, approximate slab totals
+    for r in range(world):
+        r0, r1 = sharding.slab_rows(r, world, N)
+        m = CVMatrix()
+        lib, h = m._lib, m._h
+        m.fit_begin(r1 - r0, K, M, weighted=True, max_block_rows=8192)
+        for b0 in range(r0, r1, 8192):
+            b1 = min(r1, b0 + 8192)
+            m.fit_rows(b0 - r0, X[b0:b1], Y[b0:b1], w[b0:b1])
+        ld = int(lib.cvmx_ld(h))
+        tot = torch.zeros((4 * ld,), dtype=torch.float64, device=dev)
+        app = C.c_int32(0)
+        _lib.check(lib.cvmx_slab_scan_local(h, -1, 0, vp(wg), N, r0, vp(tot), C.byref(app)), h)
+        assert app.value == 1
+        m.sync()
+        hs.append(m)
+        slabs.append((r0, r1))
+        tots.append(tot)
+    # ---- phase 2 on every slab (what the all-gather provides), then the chain of last passes
+    carry, totals, keep = None, None, []
+    for r, m in enumerate(hs):
+        lib, h = m._lib, m._h
+        start = torch.zeros_like(tots[0]) if r == 0 else torch.stack(tots[:r]).sum(0)
+        keep.append(start)
+        torch.cuda.synchronize()
+        _lib.check(lib.cvmx_slab_scan_prepare(h, -1, 0, vp(start)), h)
+    for r, m in enumerate(hs):
+        lib, h = m._lib, m._h
+        r0, r1 = slabs[r]
+        _lib.check(lib.cvmx_fit_end_slab(h, None if carry is None else vp(carry[0]), None if carry is None else vp(carry[1]), vp(wg), N, r0), h)
+        ld = int(lib.cvmx_ld(h))
+        sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_moments_ptr(h, C.byref(sp), C.byref(qp), C.byref(mc)), h)
+        carry = torch.stack([torch.as_tensor(_DevArray(sp.value, ld, "<f8"), device=dev).clone(),
+                             torch.as_tensor(_DevArray(qp.value, ld, "<f8"), device=dev).clone()])
+        tp, cnt, ldt = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(lib.cvmx_totals_ptr(h, C.byref(tp), C.byref(cnt), C.byref(ldt)), h)
+        t = torch.as_tensor(_DevArray(tp.value, cnt.value, "<f8"), device=dev)
+        totals = t.clone() if totals is None else totals + t
+    for m in hs:
+        lib, h = m._lib, m._h
+        ld = int(lib.cvmx_ld(h))
+        sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.cvmx_moments_ptr(h, C.byref(sp), C.byref(qp), C.byref(mc)), h)
+        tp, cnt, ldt = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(lib.cvmx_totals_ptr(h, C.byref(tp), C.byref(cnt), C.byref(ldt)), h)
+        torch.as_tensor(_DevArray(sp.value, ld, "<f8"), device=dev).copy_(carry[0])
+        torch.as_tensor(_DevArray(qp.value, ld, "<f8"), device=dev).copy_(carry[1])
+        torch.as_tensor(_DevArray(tp.value, cnt.value, "<f8"), device=dev).copy_(totals)
+        torch.cuda.synchronize()
+        m._streamed, m.N = True, N
+        m._pull_totals()
+        assert np.array_equal(m.sum_X, orc.sum_X) and np.array_equal(m.sum_sq_X, orc.sum_sq_X)
+        assert np.array_equal(m.sum_Y, orc.sum_Y) and np.array_equal(m.sum_sq_Y, orc.sum_sq_Y)
+        assert m.sum_w == orc.sum_w and m.num_nonzero_w == orc.nnz_w
+    # ---- folds: the same three phases for the fold sums, then statistics bit-exact against the oracle
+    ld = int(hs[0]._lib.cvmx_ld(hs[0]._h))
+    ftots = []
+    for m, (r0, r1) in zip(hs, slabs):
+        lib, h = m._lib, m._h
+        loc_off, loc_idx = sharding.local_csr(offsets, indices, r0, r1)
+        m._upload_csr(loc_off, loc_idx)
+        _lib.check(lib.cvmx_set_weight_folds(h, offsets.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p), P), h)
+        tot = torch.zeros((P * 4 * ld,), dtype=torch.float64, device=dev)
+        app = C.c_int32(0)
+        _lib.check(lib.cvmx_slab_scan_local(h, 0, P, None, 0, 0, vp(tot), C.byref(app)), h)
+        assert app.value == 1
+        m.sync()
+        ftots.append(tot)
+    for r, m in enumerate(hs):
+        start = torch.zeros_like(ftots[0]) if r == 0 else torch.stack(ftots[:r]).sum(0)
+        keep.append(start)
+        torch.cuda.synchronize()
+        _lib.check(m._lib.cvmx_slab_scan_prepare(m._h, 0, P, vp(start)), m._h)
+    raw = torch.zeros((P, 2, ld), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for m in hs:
+        _lib.check(m._lib.cvmx_slab_fold_sums(m._h, 0, P, vp(raw)), m._h)
+        m.sync()
+    m0 = hs[0]
+    _lib.check(m0._lib.cvmx_slab_finalize_stats(m0._h, 0, P, vp(raw)), m0._h)
+    m0.sync()
+    # raw fold sums against numpy's sequential sums, bit for bit
+    rawh = raw.cpu().numpy()
+    for pos, key in enumerate(part.folds_dict):
+        val = part.get_validation_indices(key)
+        Z = np.concatenate([X[val], Y[val]], axis=1)
+        WZ = w[val][:, None] * Z
+        assert np.array_equal(rawh[pos, 0, :K + M], np.sum(WZ, axis=0)), pos
+        assert np.array_equal(rawh[pos, 1, :K + M], np.sum(WZ * Z, axis=0)), pos
