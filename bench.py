@@ -711,9 +711,14 @@ def main():
         # hop) and the per-slab Grams the fold owners sum over NVLink
         slab = None
         if row_sharded and world > 1:
-            from cvmatrix_b200.distributed import RowSlabFolds
+            from cvmatrix_b200.distributed import RowSlabFolds, upload_balanced_bounds
 
-            slab = RowSlabFolds(m, N, K, M, w, block_rows=32768)
+            # slab sizes follow the copy rate each rank reaches while all ranks upload at once (set-up, outside the timed region)
+            bounds = None
+            if os.environ.get("BENCH_BALANCED_SLABS", "1") != "0":
+                n_s = min(N // world, max(8192, (128 << 20) // (8 * K)))
+                bounds = upload_balanced_bounds(N, keep[0][rank * (N // world): rank * (N // world) + n_s], dev)
+            slab = RowSlabFolds(m, N, K, M, w, block_rows=32768, bounds=bounds)
             w_pinned = torch.from_numpy(w)
 
         def e2e_step(Xh, Yh, wh, keep_results=False):
@@ -780,7 +785,7 @@ def main():
             h2d *= world
         e2e = {"value": P / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "includes": ("Partitioner + fit (H2D from pinned host memory" + ((f": 1/{world} of the rows per rank, rows stay sharded (row slabs: chained column sums, per-slab Grams summed by the fold owners over NVLink)" if slab is not None else f": 1/{world} of the rows per rank, slabs exchanged over NVLink") if world > 1 else "; fused with the fold Grams when the folds partition the rows")
+               "includes": ("Partitioner + fit (H2D from pinned host memory" + ((f": a slab of the rows per rank (sizes proportional to the measured copy rates: {[b - a for a, b in zip(bounds, bounds[1:])] if bounds else 'equal'}), rows stay sharded (row slabs: chained column sums, per-slab Grams summed by the fold owners over NVLink)" if slab is not None else f": 1/{world} of the rows per rank, slabs exchanged over NVLink") if world > 1 else "; fused with the fold Grams when the folds partition the rows")
                             + ") + set_folds + all folds + D2H of every output"),
                "host_outputs": args.e2e_out, "breakdown_ms": {k: v / e2e_steps for k, v in parts.items()}}
         if world == 1 and N * K * 8 <= 5e9 and P <= 1000:

@@ -45,6 +45,7 @@ SIGNATURES = {
     "cvmx_sharded_finish": (_i32, [_vp, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvmx_sharded_finish_peers": (_i32, [_vp, _i64, _i64, _i64, _i64, _u32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cvmx_fit_end_slab": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "cvmx_slab_begin": (_i32, [_vp, _vp, _i64, _i64]),
     "cvmx_slab_scan_local": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, C.POINTER(_i32)]),
     "cvmx_slab_scan_prepare": (_i32, [_vp, _i64, _i64, _vp]),
     "cvmx_set_weight_folds": (_i32, [_vp, _vp, _vp, _i64]),

@@ -22,7 +22,7 @@ HEADERS = ["common.cuh", "kernels_stats.cuh", "kernels_scan.cuh", "kernels_gram.
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 
 

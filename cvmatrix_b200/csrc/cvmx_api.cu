@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/cvmx.h"
@@ -104,6 +106,8 @@ struct cvmx_handle {
   int slab_scan_mode = 0;        // 0 none, 1 fit totals, 2 fold sums
   int slab_scan_stage = 0;       // 1 local passes done, 2 prepared (passes 2 and 3 done)
   int64_t slab_scan_f0 = 0, slab_scan_f1 = 0, slab_scan_csr = -1;
+  bool mass_started = false;     // cvmx_slab_begin: w_glob uploaded and the weight mass launched before the rows arrive
+  bool mass_pending = false;     // ... with the weight mass still running on side stream 2 (ev_mass)
   bool fit_pre_done = false;     // fit mode: accumulator -> totals and the weight mass already ran (cvmx_slab_scan_local)
   // streaming / sharded fit (cvmx_fit_begin / cvmx_fit_rows / cvmx_fit_end)
   bool filling = false;
@@ -995,6 +999,7 @@ int32_t fit_begin_impl(cvmx_t* h, int64_t N, int64_t K, int64_t M, int32_t weigh
   CU(h, cudaMemsetAsync(h->Ttot.p, 0, (size_t)K * ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->sum_z.p, 0, ld * sz, h->stream));
   CU(h, cudaMemsetAsync(h->sumsq_z.p, 0, ld * sz, h->stream));
+  h->mass_started = h->mass_pending = h->fit_pre_done = false; h->slab_scan_mode = h->slab_scan_stage = 0;
   if (!weighted && N > 0) { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
   const size_t smem = gram_smem_bytes<T>();
   if (!h->attr_gram) {
@@ -1178,8 +1183,10 @@ struct SlabArgs { const void* carry_sum; const void* carry_sumsq; const void* w_
 
 // The part of cvmx_fit_end that does not depend on the moment chains: accumulator -> totals, weight mass.
 // use_w_glob: the weight mass runs over h->w_glob (row slabs: all N_w weights of the data set).
+// mass_aside: the weight mass (ONE CTA walking numpy's pairwise tree over all N_w weights: ~1 ms at N = 1M) runs on side
+// stream 2 instead of the main stream; the caller joins h->ev_mass before it reads fit_scal.
 template <typename T>
-int32_t fit_end_pre(cvmx_t* h, bool use_w_glob, int64_t N_w) {
+int32_t fit_end_pre(cvmx_t* h, bool use_w_glob, int64_t N_w, bool mass_aside = false) {
   const int64_t K = h->K, M = h->M, ld = h->ld;
   // accumulator -> totals (raw epilogue: mirrored XtWX, XtWY)
   std::vector<int2> tiles;
@@ -1203,11 +1210,19 @@ int32_t fit_end_pre(cvmx_t* h, bool use_w_glob, int64_t N_w) {
   h->launches++;
   CU(h, cudaGetLastError());
   // statistics over all rows: weight mass everywhere, moment sums for this column shard (others stay zero)
-  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->stream>>>(h->Z.as<T>(), use_w_glob && h->weighted ? h->w_glob.as<T>() : h->w.as<T>(), ld,
+  if (h->mass_started) { h->mass_started = false; return CVMX_OK; }   // cvmx_slab_begin launched it beside the upload
+  cudaStream_t ms = h->stream;
+  if (mass_aside) {
+    CU(h, cudaEventRecord(h->ev_mass, h->stream));
+    CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+    ms = h->aux2_stream;
+  }
+  k_weight_mass<T, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, ms>>>(h->Z.as<T>(), use_w_glob && h->weighted ? h->w_glob.as<T>() : h->w.as<T>(), ld,
                                                                           N_w, K, M, h->weighted ? 1 : 0, nullptr, nullptr, 0, 1,
                                                                           h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<T>());
   h->launches++;
   CU(h, cudaGetLastError());
+  if (mass_aside) { CU(h, cudaEventRecord(h->ev_mass, h->aux2_stream)); h->mass_pending = true; }
   return CVMX_OK;
 }
 
@@ -1216,7 +1231,7 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
   const int64_t N = h->N, K = h->K, M = h->M, ld = h->ld;
   if (sl) {
     // row-slab mode: the weight sums need every weight of the data set, the moment chains continue the previous slab's
-    if (h->weighted && !h->fit_pre_done) {
+    if (h->weighted && !h->fit_pre_done && !h->mass_started) {
       CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(sl->N_glob, 1) * sizeof(T)));
       CU(h, cudaMemcpyAsync(h->w_glob.p, sl->w_glob, (size_t)sl->N_glob * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     }
@@ -1245,6 +1260,7 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
   }
   h->slab_scan_mode = 0; h->slab_scan_stage = 0;
   if (rc) return rc;
+  if (h->mass_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0)); h->mass_pending = false; }
   FitScalars fsc;
   CU(h, cudaMemcpyAsync(&fsc, h->fit_scal.p, sizeof(fsc), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -2032,6 +2048,34 @@ int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_su
   return h->dtype == CVMX_F64 ? fit_end_impl<double>(h, 0, 1, &sl) : fit_end_impl<float>(h, 0, 1, &sl);
 }
 
+int32_t cvmx_slab_begin(cvmx_t* h, const void* w_glob, int64_t N_glob, int64_t row0) {
+  if (!h || !h->filling) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_begin: call cvmx_fit_begin first");
+  if (N_glob < h->N || row0 < 0 || row0 + h->N > N_glob || (h->weighted && !w_glob)) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_begin: bad slab arguments");
+  if (h->K < 2 || h->M == 1) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_begin: row slabs need K >= 2 and M != 1");
+  ON_DEVICE(h);
+  const size_t sz = esz(h);
+  if (h->weighted) {
+    CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(N_glob, 1) * sz));
+    CU(h, cudaMemcpyAsync(h->w_glob.p, w_glob, (size_t)N_glob * sz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->slab = true; h->N_glob = N_glob; h->row0 = row0;
+  CU(h, cudaEventRecord(h->ev_mass, h->stream));
+  CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+  if (h->dtype == CVMX_F64)
+    k_weight_mass<double, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->aux2_stream>>>(
+        h->Z.as<double>(), h->weighted ? h->w_glob.as<double>() : h->w.as<double>(), h->ld, N_glob, h->K, h->M, h->weighted ? 1 : 0, nullptr, nullptr, 0,
+        1, h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<double>());
+  else
+    k_weight_mass<float, PW_LEVELS_BIG><<<1, 1 << PW_LEVELS_BIG, 0, h->aux2_stream>>>(
+        h->Z.as<float>(), h->weighted ? h->w_glob.as<float>() : h->w.as<float>(), h->ld, N_glob, h->K, h->M, h->weighted ? 1 : 0, nullptr, nullptr, 0,
+        1, h->ddof, h->fit_scal.as<FitScalars>(), nullptr, h->pwcols.as<float>());
+  h->launches++;
+  CU(h, cudaGetLastError());
+  CU(h, cudaEventRecord(h->ev_mass, h->aux2_stream));
+  h->mass_started = true; h->mass_pending = true;
+  return CVMX_OK;
+}
+
 int32_t cvmx_slab_scan_local(cvmx_t* h, int64_t f0, int64_t f1, const void* w_glob, int64_t N_glob, int64_t row0, double* tot_out,
                              int32_t* applicable) {
   if (!h || !tot_out || !applicable) return fail(h, CVMX_ERR_INVALID, "cvmx_slab_scan_local: null argument");
@@ -2050,12 +2094,12 @@ int32_t cvmx_slab_scan_local(cvmx_t* h, int64_t f0, int64_t f1, const void* w_gl
   bool app = false;
   if (fit_mode) {
     // everything of cvmx_fit_end_slab that does not depend on the previous slab: global weights, accumulator -> totals, weight mass
-    if (h->weighted) {
+    if (h->weighted && !h->mass_started) {
       CU(h, h->w_glob.reserve((size_t)std::max<int64_t>(N_glob, 1) * sizeof(double)));
       CU(h, cudaMemcpyAsync(h->w_glob.p, w_glob, (size_t)N_glob * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
     h->slab = true; h->N_glob = N_glob; h->row0 = row0;
-    int32_t rp = fit_end_pre<double>(h, true, N_glob);
+    int32_t rp = fit_end_pre<double>(h, true, N_glob, true);
     if (rp) return rp;
     h->fit_pre_done = true;
   }
@@ -2144,9 +2188,9 @@ int32_t cvmx_profile_read(cvmx_t* h, double* ms, int64_t* count) {
 
 // Host-side CSR builder for integer fold labels (no device work): labels in [lo, lo + span) -> fold order by first
 // appearance, offsets and ascending row indices, in two O(N) counting passes.  scratch: 2 * span int64.
-int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch,
-                              int64_t* first_rows /* span */, int64_t* offsets /* span + 1 */, int64_t* indices /* n */) {
-  if (!labels || n < 0 || span <= 0 || !scratch || !first_rows || !offsets || !indices) return -1;
+// Serial form: two passes, folds numbered by first appearance.
+static int64_t partition_labels_serial(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch, int64_t* first_rows,
+                                       int64_t* offsets, int64_t* indices) {
   int64_t* slot = scratch;          // label -> fold position (-1: unseen)
   int64_t* count = scratch + span;  // per fold position
   for (int64_t l = 0; l < span; ++l) { slot[l] = -1; count[l] = 0; }
@@ -2162,6 +2206,81 @@ int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int6
   for (int64_t s = 0; s < n_folds; ++s) { offsets[s + 1] = offsets[s] + count[s]; count[s] = offsets[s]; }
   for (int64_t i = 0; i < n; ++i) indices[count[slot[labels[i] - lo]]++] = i;
   return n_folds;
+}
+
+// Threaded form for long label arrays with few distinct labels (K-fold / leave-many-out at N = 1M: the serial passes are
+// 2-3 ms of a 20-80 ms end-to-end step): every thread histograms a contiguous chunk of the rows and notes the first row of
+// each label it sees; the chunks' histograms give every (chunk, fold) its own output range, so the scatter is parallel,
+// stable, and needs no atomics.  Same result as the serial form, element for element.
+static int64_t partition_labels_threaded(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch, int64_t* first_rows,
+                                         int64_t* offsets, int64_t* indices, int nthreads) {
+  std::vector<int64_t> hist((size_t)nthreads * span, 0), first((size_t)nthreads * span, -1);
+  std::vector<int> bad((size_t)nthreads, 0);
+  auto chunk = [&](int t) { return std::make_pair(n * t / nthreads, n * (t + 1) / nthreads); };
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        int64_t* h = hist.data() + (size_t)t * span;
+        int64_t* f = first.data() + (size_t)t * span;
+        const auto [b, e] = chunk(t);
+        for (int64_t i = b; i < e; ++i) {
+          const int64_t l = labels[i] - lo;
+          if (l < 0 || l >= span) { bad[t] = 1; return; }
+          if (h[l]++ == 0) f[l] = i;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < nthreads; ++t) if (bad[t]) return -1;
+  int64_t* slot = scratch;          // label -> fold position (-1: unseen)
+  int64_t* count = scratch + span;  // label -> number of rows
+  std::vector<std::pair<int64_t, int64_t>> seen;   // (first row, label)
+  for (int64_t l = 0; l < span; ++l) {
+    int64_t fr = -1, c = 0;
+    for (int t = 0; t < nthreads; ++t) {
+      c += hist[(size_t)t * span + l];
+      if (fr < 0) fr = first[(size_t)t * span + l];   // chunks are in row order: the first chunk that saw the label
+    }
+    slot[l] = -1; count[l] = c;
+    if (c > 0) seen.emplace_back(fr, l);
+  }
+  std::sort(seen.begin(), seen.end());
+  const int64_t n_folds = (int64_t)seen.size();
+  offsets[0] = 0;
+  for (int64_t s = 0; s < n_folds; ++s) {
+    slot[seen[s].second] = s; first_rows[s] = seen[s].first;
+    offsets[s + 1] = offsets[s] + count[seen[s].second];
+  }
+  // hist[t][l] -> first output position of chunk t's rows of label l
+  for (int64_t l = 0; l < span; ++l) {
+    if (slot[l] < 0) continue;
+    int64_t pos = offsets[slot[l]];
+    for (int t = 0; t < nthreads; ++t) { const int64_t c = hist[(size_t)t * span + l]; hist[(size_t)t * span + l] = pos; pos += c; }
+  }
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        int64_t* pos = hist.data() + (size_t)t * span;
+        const auto [b, e] = chunk(t);
+        for (int64_t i = b; i < e; ++i) indices[pos[labels[i] - lo]++] = i;
+      });
+    for (auto& x : th) x.join();
+  }
+  return n_folds;
+}
+
+int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch,
+                              int64_t* first_rows /* span */, int64_t* offsets /* span + 1 */, int64_t* indices /* n */) {
+  if (!labels || n < 0 || span <= 0 || !scratch || !first_rows || !offsets || !indices) return -1;
+  int nthreads = 1;
+  if (n >= 200000 && span <= 4096) {
+    nthreads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = std::getenv("CVMX_PARTITION_THREADS")) nthreads = std::max(1, std::min(64, std::atoi(e)));
+  }
+  if (nthreads == 1) return partition_labels_serial(labels, n, lo, span, scratch, first_rows, offsets, indices);
+  return partition_labels_threaded(labels, n, lo, span, scratch, first_rows, offsets, indices, nthreads);
 }
 
 int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }

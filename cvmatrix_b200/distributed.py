@@ -238,6 +238,36 @@ def fit_sharded_upload(cvm: CVMatrix, X, Y=None, weights=None, group=None, block
     cvm.weights = None if w is None else w.reshape(-1, 1)
 
 
+def upload_balanced_bounds(N: int, sample, device, group=None, reps: int = 3):
+    """Slab boundaries proportional to the host->device copy rate every rank reaches WHILE ALL RANKS COPY AT ONCE.
+
+    On an 8-GPU box the links to host memory are not equal once they are all busy (measured on this pool's B200 boxes,
+    0.5 GB per rank from pinned memory: 23 GB/s on four GPUs, 35 GB/s on the other four, against 55 GB/s for one GPU
+    alone), and a row-sharded fit is as slow as its slowest upload.  `sample`: a pinned host tensor of this rank (>= 64 MB;
+    a slice of the data itself will do).  Collective: every rank of `group` must call it.  Returns a list of W + 1 rows."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [0, int(N)]
+    dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+    buf = torch.empty(sample.shape, dtype=sample.dtype, device=dev)
+    buf.copy_(sample, non_blocking=True)                      # warm-up (page tables, first-touch)
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        buf.copy_(sample, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    rate = torch.tensor([sample.numel() * sample.element_size() * reps / max(e0.elapsed_time(e1), 1e-3)], dtype=torch.float64, device=dev)
+    rates = torch.empty((world,), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(rates, rate, group=group)
+    return sharding.weighted_slab_bounds(rates.tolist(), int(N))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Row-slab mode (BASELINE config 5): the ROWS of the data set are sharded across the ranks instead of replicated.
 # ---------------------------------------------------------------------------------------------------------------------
@@ -259,7 +289,7 @@ class RowSlabFolds:
     * weight sums (pairwise trees over all rows): every rank holds the whole weight vector and evaluates them itself.
     """
 
-    def __init__(self, cvm: CVMatrix, N: int, K: int, M: int, weights=None, group=None, block_rows: int = 65536):
+    def __init__(self, cvm: CVMatrix, N: int, K: int, M: int, weights=None, group=None, block_rows: int = 65536, bounds=None):
         import torch
         import torch.distributed as dist
 
@@ -270,7 +300,13 @@ class RowSlabFolds:
         self.f64 = np.dtype(cvm.dtype) == np.float64
         self.tdt = torch.float64 if self.f64 else torch.float32
         self.N, self.K, self.M = int(N), int(K), int(M or 0)
-        self.row0, self.row1 = sharding.slab_rows(self.rank, self.world, self.N)
+        # bounds: slab boundaries b_0 .. b_W agreed by all ranks (upload_balanced_bounds); default: equal slabs
+        if bounds is not None:
+            if len(bounds) != self.world + 1 or bounds[0] != 0 or bounds[-1] != self.N or any(a > b for a, b in zip(bounds, bounds[1:])):
+                raise ValueError("bounds must be world + 1 ascending row numbers from 0 to N")
+            self.row0, self.row1 = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        else:
+            self.row0, self.row1 = sharding.slab_rows(self.rank, self.world, self.N)
         self.block_rows = int(block_rows)
         self.w_host = None
         if weights is not None and not hasattr(weights, "data_ptr"):
@@ -307,8 +343,22 @@ class RowSlabFolds:
     def fit(self, blocks) -> None:
         t, dist, cvm = self.torch, self.dist, self.cvm
         lib, h = cvm._lib, cvm._h
+        import os
+        import time
+
+        timing = os.environ.get("CVMX_SLAB_TIMING", "0") != "0"     # diagnostic: per-phase wall times (adds synchronisations)
+        marks = []
+
+        def mark(name):
+            if timing:
+                t.cuda.synchronize(self.dev)
+                marks.append((name, time.perf_counter()))
+
+        mark("begin")
         n_local = self.row1 - self.row0
         cvm.fit_begin(n_local, self.K, self.M, weighted=self.w is not None, max_block_rows=self.block_rows)
+        # the weight sums (one CTA over all N weights) run on a side stream while the rows upload
+        _lib.check(lib.cvmx_slab_begin(h, None if self.w is None else C.c_void_p(self.w.data_ptr()), self.N, self.row0), h)
         for b0, Xb, Yb in blocks:
             nb = int(Xb.shape[0])
             if b0 < self.row0 or b0 + nb > self.row1:
@@ -324,12 +374,15 @@ class RowSlabFolds:
             cvm.fit_rows(b0 - self.row0, Xb, Yb if self.M else None, wb, gram=True)
         ld = int(lib.cvmx_ld(h))
         vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())  # noqa: E731
+        mark("rows")
         # decoupled chain: every rank runs the streaming scan passes of its slab now; only the last pass waits for the carry
         self._decoupled(-1, 0, 1, ld, w_args=(vp(self.w), self.N, self.row0))
+        mark("scan")
         carry = t.zeros((2, ld), dtype=self.tdt, device=self.dev)
         if self.world > 1 and self.rank > 0:
             dist.recv(carry, src=self._grank(self.rank - 1), group=self.group)
             t.cuda.current_stream(self.dev).synchronize()
+        mark("recv")
         first = self.rank == 0
         _lib.check(lib.cvmx_fit_end_slab(h, None if first else vp(carry[0]), None if first else vp(carry[1]), vp(self.w), self.N, self.row0), h)
         sp, qp, mc = C.c_void_p(), C.c_void_p(), C.c_int64()
@@ -337,6 +390,7 @@ class RowSlabFolds:
         ts = "<f8" if self.f64 else "<f4"
         sum_z = t.as_tensor(_DevArray(sp.value, ld, ts), device=self.dev)
         sumsq_z = t.as_tensor(_DevArray(qp.value, ld, ts), device=self.dev)
+        mark("fit_end")
         if self.world > 1:
             carry[0].copy_(sum_z)
             carry[1].copy_(sumsq_z)
@@ -350,9 +404,16 @@ class RowSlabFolds:
             dist.all_reduce(t.as_tensor(_DevArray(tp.value, cnt.value, ts), device=self.dev), group=self.group)
             t.cuda.current_stream(self.dev).synchronize()
             _lib.check(lib.cvmx_commit_totals(h), h)
+        mark("collectives")
         cvm._streamed = True
         cvm.N = self.N
         cvm._pull_totals()
+        mark("pull")
+        if timing and marks:
+            import sys
+
+            print(f"[slab fit rank {self.rank}] " + " ".join(f"{b[0]}={1e3 * (b[1] - a[1]):.2f}ms" for a, b in zip(marks, marks[1:])),
+                  file=sys.stderr, flush=True)
 
     def _decoupled(self, f0: int, f1: int, n_sets: int, ld: int, w_args=(None, 0, 0)) -> bool:
         """Streaming passes of the binade scan for the fit totals (f0 < 0) or the folds [f0, f1) of this slab, before the
@@ -381,13 +442,14 @@ class RowSlabFolds:
         from .partitioner import Partitioner
 
         cvm = self.cvm
-        if isinstance(folds, Partitioner):
+        is_part = isinstance(folds, Partitioner)
+        if is_part:
             offsets, indices = folds.csr()
         else:
             offsets, indices = folds
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int64)
-        loc_off, loc_idx = sharding.local_csr(offsets, indices, self.row0, self.row1)
+        loc_off, loc_idx = sharding.local_csr(offsets, indices, self.row0, self.row1, assume_sorted=is_part)
         cvm._upload_csr(loc_off, loc_idx)
         _lib.check(cvm._lib.cvmx_set_weight_folds(cvm._h, offsets.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
                                                   offsets.size - 1), cvm._h)

@@ -46,21 +46,57 @@ def slab_rows(rank: int, world: int, n_rows: int):
     return rank * n_rows // world, (rank + 1) * n_rows // world
 
 
-def local_csr(offsets, indices, row0: int, row1: int):
+def weighted_slab_bounds(weights, n_rows: int, align: int = GRAM_ROW_ALIGN):
+    """Row-slab boundaries [b_0 = 0, ..., b_W = n_rows] with slab r proportional to weights[r] (e.g. the host->device copy
+    rate each rank measured: on a box whose GPUs do not reach host memory equally fast, equal slabs make every fit wait
+    for the slowest link).  Boundaries are multiples of `align` rows; every rank keeps at least one aligned block when
+    the data set allows it."""
+    w = [max(float(x), 0.0) for x in weights]
+    world = len(w)
+    total = sum(w)
+    if total <= 0.0:
+        w, total = [1.0] * world, float(world)
+    bounds, acc = [0], 0.0
+    for r in range(world - 1):
+        acc += w[r]
+        b = int(round(n_rows * acc / total / align)) * align
+        lo = bounds[-1] + (align if n_rows >= world * align else 0)
+        hi = n_rows - (world - 1 - r) * (align if n_rows >= world * align else 0)
+        bounds.append(max(lo, min(b, hi)))
+    bounds.append(n_rows)
+    return bounds
+
+
+def local_csr(offsets, indices, row0: int, row1: int, assume_sorted: bool = False):
     """The part of a global CSR of validation sets (ascending row numbers inside every fold) that falls into the row slab
     [row0, row1), renumbered from 0: (local offsets, local indices).  Raises if a fold is not ascending - the chained
-    column sums rely on a fold's rows on rank r all preceding those on rank r + 1."""
+    column sums rely on a fold's rows on rank r all preceding those on rank r + 1 (``assume_sorted``: the caller vouches
+    for it - a Partitioner's index sets are ascending by construction - and the check, a pass over all N indices, is
+    skipped)."""
     import numpy as np
 
     offsets = np.asarray(offsets, dtype=np.int64)
     indices = np.asarray(indices, dtype=np.int64)
     P = offsets.size - 1
-    parts, loc = [], np.zeros(P + 1, np.int64)
-    for f in range(P):
-        idx = indices[offsets[f]:offsets[f + 1]]
-        if idx.size > 1 and np.any(np.diff(idx) <= 0):
-            raise ValueError(f"fold {f}: row-slab mode needs strictly ascending validation indices")
-        lo, hi = np.searchsorted(idx, row0), np.searchsorted(idx, row1)
-        parts.append(idx[lo:hi] - row0)
-        loc[f + 1] = loc[f] + (hi - lo)
-    return loc, (np.concatenate(parts) if parts else np.zeros(0, np.int64))
+    loc = np.zeros(P + 1, np.int64)
+    if not assume_sorted and indices.size > 1:
+        step = np.diff(indices) <= 0
+        step[offsets[1:-1][(offsets[1:-1] > 0) & (offsets[1:-1] < indices.size)] - 1] = False   # fold boundaries may step down
+        if step.any():
+            bad = int(np.searchsorted(offsets, np.flatnonzero(step)[0], side="right") - 1)
+            raise ValueError(f"fold {bad}: row-slab mode needs strictly ascending validation indices")
+    if P <= 4096:
+        lo = np.empty(P, np.int64)
+        hi = np.empty(P, np.int64)
+        for f in range(P):
+            idx = indices[offsets[f]:offsets[f + 1]]
+            lo[f], hi[f] = np.searchsorted(idx, row0), np.searchsorted(idx, row1)
+        np.cumsum(hi - lo, out=loc[1:])
+        out = np.empty(int(loc[P]), np.int64)
+        for f in range(P):
+            np.subtract(indices[offsets[f] + lo[f]:offsets[f] + hi[f]], row0, out=out[loc[f]:loc[f + 1]])
+        return loc, out
+    inside = (indices >= row0) & (indices < row1)            # many folds: one vectorised pass, order preserved
+    csum = np.concatenate([[0], np.cumsum(inside)])
+    loc[:] = csum[offsets]
+    return loc, indices[inside] - row0

@@ -250,6 +250,10 @@ int32_t cvmx_fit_end_slab(cvmx_t* h, const void* carry_sum, const void* carry_su
  *                            chained calls.  Every rank must take the same path (all-reduce the flag).
  *   cvmx_slab_scan_prepare : start = the sum of tot_out over all EARLIER slabs (zeros on the first), same layout.
  *   then cvmx_fit_end_slab / cvmx_slab_fold_sums with the exact carry as before: they run only the last pass. */
+/* Optional, right after cvmx_fit_begin of a row slab: hands over the global weights early (same w_glob / N_glob / row0 as
+ * the cvmx_fit_end_slab that follows) so that the weight sums - ONE CTA walking numpy's pairwise tree over all N_glob
+ * weights (cvmatrix/cvmatrix.py:1219-1229), ~1 ms at N = 1M - run on a side stream while the rows are still uploading. */
+int32_t cvmx_slab_begin(cvmx_t* h, const void* w_glob, int64_t N_glob, int64_t row0);
 int32_t cvmx_slab_scan_local(cvmx_t* h, int64_t f0, int64_t f1, const void* w_glob, int64_t N_glob, int64_t row0, double* tot_out,
                              int32_t* applicable);
 int32_t cvmx_slab_scan_prepare(cvmx_t* h, int64_t f0, int64_t f1, const double* start);

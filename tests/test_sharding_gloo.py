@@ -118,3 +118,16 @@ def test_row_slab_csr_covers_every_fold_once():
 
     with pytest.raises(ValueError, match="ascending"):
         sharding.local_csr(np.array([0, 3]), np.array([5, 2, 9]), 0, 10)
+
+
+def test_weighted_slab_bounds():
+    from cvmatrix_b200 import sharding
+
+    b = sharding.weighted_slab_bounds([23, 23, 23, 23, 35, 35, 35, 35], 1_000_000)
+    assert b[0] == 0 and b[-1] == 1_000_000 and len(b) == 9 and all(x % 16 == 0 for x in b[:-1])
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert all(s > 0 for s in sizes) and abs(sizes[4] / sizes[0] - 35 / 23) < 0.01
+    assert sharding.weighted_slab_bounds([1, 1], 100) == [0, 48, 100]
+    assert sharding.weighted_slab_bounds([0, 0, 0], 50) == [0, 16, 32, 50]           # no rates: equal slabs
+    assert sharding.weighted_slab_bounds([1, 0, 1, 5], 64) == [0, 16, 32, 48, 64]    # every rank keeps a block
+    assert sharding.weighted_slab_bounds([3.0], 10) == [0, 10]
