@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/cvmx.h"
+#include "host_stager.h"
 #include "kernels_gram.cuh"
 #include "kernels_gram_tc.cuh"
 #include "kernels_stats.cuh"
@@ -121,6 +122,10 @@ struct cvmx_handle {
   int f32_tc = 1;
   int fmap = 0;
   bool attr_tc = false;
+  // contiguous uploads from PAGEABLE host memory go through a page-locked ring filled by worker threads (host_stager.h);
+  // CVMX_HOST_STAGER=0 leaves them to the driver's bounce buffer
+  HostStager* stager = nullptr;
+  int use_stager = 1;
   int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
   int64_t scan_launches = 0;
   int64_t launches = 0;
@@ -177,6 +182,16 @@ int prof_mark(cvmx_t* h) {
 }
 void prof_span(cvmx_t* h, int kind, int a, int b) {
   if (h->prof && a >= 0 && b >= 0) h->prof_spans.push_back({kind, {a, b}});
+}
+
+// Contiguous host -> device copy on `stream`: page-locked sources go straight to the DMA engine; large pageable ones through
+// the stager (`pageable`: the caller looked the source up once per call).
+inline cudaError_t h2d_copy(cvmx_t* h, void* dst, const void* src, size_t bytes, cudaStream_t stream, bool pageable) {
+  if (pageable && h->use_stager && bytes >= ((size_t)4 << 20)) {
+    if (!h->stager) h->stager = new HostStager();
+    return h->stager->copy(dst, src, bytes, stream);
+  }
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
 
 inline size_t esz(const cvmx_t* h) { return h->dtype == CVMX_F64 ? 8 : 4; }
@@ -702,11 +717,12 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
     if (M > 0 && !stage_y) CU(h, cudaMemcpy2DAsync(Z + K, ld * sz, Y, ldy * sz, M * sz, N, kind, h->stream));
     if (stage_y) {
       CU(h, h->out_xy.reserve((size_t)N * M * sz));   // scratch (reused by host-output fold batches later)
-      CU(h, cudaMemcpyAsync(h->out_xy.p, Y, (size_t)N * M * sz, cudaMemcpyHostToDevice, h->stream));
+      CU(h, h2d_copy(h, h->out_xy.p, Y, (size_t)N * M * sz, h->stream, HostStager::pageable(Y)));
       k_repack<T><<<h->sm_count * 4, 256, 0, h->stream>>>(h->out_xy.as<T>(), N, M, Z + K, ld);
       h->launches++;
     }
-    if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
+    if (w && mem == CVMX_HOST) CU(h, h2d_copy(h, h->w.p, w, N * sz, h->stream, HostStager::pageable(w)));
+    else if (w) CU(h, cudaMemcpyAsync(h->w.p, w, N * sz, kind, h->stream));
     else { k_fill<T><<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->w.as<T>(), N, T(1)); h->launches++; }
   }
   CU(h, cudaMemsetAsync(h->Ttot.p, 0, (size_t)K * ld * sz, h->stream));
@@ -874,12 +890,13 @@ int32_t fit_impl(cvmx_t* h, const void* X, int64_t N, int64_t K, int64_t ldx, co
     CU(h, h->stage[1].reserve((size_t)chunk_rows * K * sz));
     CU(h, cudaEventRecord(h->ev_mass, h->stream));                    // Y, w, pad and the unit table are queued
     CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_mass, 0));
+    const bool x_pageable = HostStager::pageable(X);
     int c = 0;
     for (int64_t r0 = 0; r0 < N; r0 += chunk_rows, ++c) {
       const int64_t nr = std::min(chunk_rows, N - r0);
       const int b = c & 1;
       if (c >= 2) CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[b], 0));       // staging buffer free again
-      CU(h, cudaMemcpyAsync(h->stage[b].p, (const char*)X + (size_t)r0 * K * sz, (size_t)nr * K * sz, cudaMemcpyHostToDevice, h->aux2_stream));
+      CU(h, h2d_copy(h, h->stage[b].p, (const char*)X + (size_t)r0 * K * sz, (size_t)nr * K * sz, h->aux2_stream, x_pageable));
       CU(h, cudaEventRecord(h->ev_copied[b], h->aux2_stream));
       CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
       k_repack<T><<<h->sm_count * 8, 256, 0, h->stream>>>(h->stage[b].as<T>(), nr, K, Z + r0 * ld, ld);
@@ -1029,9 +1046,9 @@ int32_t fit_rows_impl(cvmx_t* h, int64_t row0, int64_t nr, const void* X, int64_
     CU(h, h->stage[cb].reserve(std::max<size_t>(xb + yb, 16)));
     CU(h, cudaStreamWaitEvent(h->aux2_stream, h->ev_stage[cb], 0));      // the kernels that read this buffer two calls ago
     char* st = h->stage[cb].as<char>();
-    if (cx) CU(h, cudaMemcpyAsync(st, X, xb, cudaMemcpyHostToDevice, h->aux2_stream));
+    if (cx) CU(h, h2d_copy(h, st, X, xb, h->aux2_stream, HostStager::pageable(X)));
     else CU(h, cudaMemcpy2DAsync(Zb, ld * sz, X, ldx * sz, K * sz, nr, cudaMemcpyHostToDevice, h->aux2_stream));
-    if (cy) CU(h, cudaMemcpyAsync(st + xb, Y, yb, cudaMemcpyHostToDevice, h->aux2_stream));
+    if (cy) CU(h, h2d_copy(h, st + xb, Y, yb, h->aux2_stream, HostStager::pageable(Y)));
     else if (M > 0) CU(h, cudaMemcpy2DAsync(Zb + K, ld * sz, Y, ldy * sz, M * sz, nr, cudaMemcpyHostToDevice, h->aux2_stream));
     if (h->weighted) CU(h, cudaMemcpyAsync(h->w.as<T>() + row0, w, nr * sz, cudaMemcpyHostToDevice, h->aux2_stream));
     CU(h, cudaEventRecord(h->ev_copied[cb], h->aux2_stream));
@@ -1693,6 +1710,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_SCAN_SPEC")) h->scan_spec = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_HOST_STAGER")) h->use_stager = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_F32_TC")) h->f32_tc = std::max(0, std::min(2, std::atoi(e)));
   DeviceGuard guard__(device);
   if ((e = guard__.err) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -1727,6 +1745,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
   h->tc_gram.release(); h->tc_finish.release();
+  delete h->stager; h->stager = nullptr;
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
   if (h->aux2_stream) { cudaStreamSynchronize(h->aux2_stream); cudaStreamDestroy(h->aux2_stream); }
