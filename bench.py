@@ -336,11 +336,16 @@ def time_fold_path(ctx, m, P, steps, warmup, sf=None, row_sharded=False, clocks=
     ctx.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profiled = os.environ.get("BENCH_CUDA_PROFILER", "0") != "0"   # ncu --profile-from-start off: only the timed steps are captured
+    if profiled:
+        torch.cuda.profiler.start()
     e0.record(ctx.stream)
     for _ in range(steps):
         step()
     e1.record(ctx.stream)
     torch.cuda.synchronize()
+    if profiled:
+        torch.cuda.profiler.stop()
     ctx.barrier()
     ms = e0.elapsed_time(e1)
     clk = sampler.stop() if sampler else None
@@ -393,7 +398,8 @@ def roofline_of(cfg_name, cfg, world, rank_rows, rank_folds, timing, ms_per_step
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        roof["traffic"] = tj.get(cfg_name if world == 1 else f"{cfg_name}@{world}")   # ncu capture of the same per-rank launch
+        shards = int(os.environ.get("BENCH_EMULATE_SHARDS", "0")) or world
+        roof["traffic"] = tj.get(cfg_name if shards == 1 else f"{cfg_name}@{shards}")   # ncu capture of the same per-rank launch
     except Exception:
         pass
     return roof
@@ -467,11 +473,16 @@ def run_row_slabs(args, cfg, ctx):
     ctx.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profiled = os.environ.get("BENCH_CUDA_PROFILER", "0") != "0"   # ncu --profile-from-start off: only the timed steps are captured
+    if profiled:
+        torch.cuda.profiler.start()
     e0.record(ctx.stream)
     for _ in range(steps):
         step()
     e1.record(ctx.stream)
     torch.cuda.synchronize()
+    if profiled:
+        torch.cuda.profiler.stop()
     ctx.barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
@@ -798,7 +809,8 @@ def main():
             torch.cuda.synchronize()
             dtp = (time.perf_counter() - t0) / 2
             e2e["pageable_input"] = {"value": P / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": 2,
-                                     "note": "inputs are ordinary numpy arrays: the driver stages pageable memory through its bounce buffer"}
+                                     "note": "inputs are ordinary (pageable) numpy arrays: the library stages them through its page-locked ring filled by worker threads "
+                                             "(csrc/host_stager.h; CVMX_HOST_STAGER=0 = the driver's bounce buffer, ~370 ms)"}
             del Xp, Yp, wp
 
     # ---- CPU baseline + parity: the reference on this box's host cores (rank 0) --------------------------------
