@@ -1,15 +1,13 @@
 set -x
 mkdir -p gpurun_out
-T=${1:-r02w}
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/${T}_pytest.txt; cat gpurun_out/${T}_pytest.txt
-timeout 500 python bench.py > gpurun_out/${T}_bench_cfg2.json 2> gpurun_out/${T}_bench_cfg2.err
-CVMX_HOST_STAGER=0 timeout 500 python bench.py --no-also --no-cpu-baseline --steps 5 > gpurun_out/${T}_bench_cfg2_nostager.json 2> gpurun_out/${T}_bench_cfg2_nostager.err
-for t in 2 4 8 16; do CVMX_STAGE_THREADS=$t timeout 300 python bench.py --no-also --no-cpu-baseline --steps 5 > gpurun_out/${T}_bench_cfg2_t$t.json 2>/dev/null; done
-python - <<P
-import json,glob
-for f in sorted(glob.glob('gpurun_out/${T}_bench_cfg2*.json')):
-  for line in open(f):
+T=${1:-r02x}
+timeout 600 python -m pytest tests/test_gpu_host_stager.py -x -q 2>&1 | tail -5 > gpurun_out/${T}_pytest.txt; cat gpurun_out/${T}_pytest.txt
+for s in 0 1 2 0 1 2; do
+  CVMX_LOO_STORE=$s timeout 300 python bench.py --config cfg4 --steps 8 --no-e2e --no-cpu-baseline --no-parity > gpurun_out/${T}_cfg4_s$s.json 2>/dev/null
+  python - <<P
+import json
+for line in open('gpurun_out/${T}_cfg4_s$s.json'):
     if line.startswith('{'):
-        d=json.loads(line); print(f, round(d['value'],1), round(d['e2e']['value'],2), d['e2e']['breakdown_ms']['partitioner_ms'], d['e2e'].get('pageable_input'))
+        d=json.loads(line); print('store hint $s', round(d['value']), round(d['ms_per_step'],4), round(d['roofline']['kernel_ms_per_step'],4), round(d['roofline']['write_gbs']))
 P
-timeout 900 python tools/parity_report.py > gpurun_out/${T}_parity.log 2>&1; tail -3 gpurun_out/${T}_parity.log
+done
