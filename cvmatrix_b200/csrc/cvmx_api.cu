@@ -10,9 +10,9 @@
 
 #include "../../include/cvmx.h"
 #include "host_stager.h"
+#include "kernels_stats.cuh"
 #include "kernels_gram.cuh"
 #include "kernels_gram_tc.cuh"
-#include "kernels_stats.cuh"
 #include "kernels_scan.cuh"
 #include <cstdlib>
 #include <type_traits>
@@ -85,7 +85,7 @@ struct cvmx_handle {
   // scratch
   DevBuf units, tiles, fold_units, split_folds, partials, stats, rawsums, fscal, pwcols, errflag, out_xx, out_xy, out_small;
   Plan plan;
-  bool attr_gram = false, attr_mom = false;
+  bool attr_gram = false, attr_mom = false, attr_gram_fused = false;
   // binade scan of the moment chains (kernels_scan.cuh): 0 off, 1 when the chains are the critical path, 2 always
   int scan_mode = 1;
   // leave-one-out batches: 0 streaming form (two FMAs + reciprocal scaling per element, matrices to ~1e-15 of the
@@ -124,6 +124,9 @@ struct cvmx_handle {
   bool attr_tc = false;
   // contiguous uploads from PAGEABLE host memory go through a page-locked ring filled by worker threads (host_stager.h);
   // CVMX_HOST_STAGER=0 leaves them to the driver's bounce buffer
+  // fold statistics inside the Gram kernel for batches of single-unit folds (GramParams::fuse_stats); CVMX_FUSE_STATS=0: separate pass
+  int fuse_stats = 1;
+  DevBuf stat_flags;
   HostStager* stager = nullptr;
   int use_stager = 1;
   int scan_spec = 1;    // fold statistics: passes 1 and 3 in one read of the rows from guessed proxies (k_scan_spec); 0: four passes
@@ -188,8 +191,12 @@ void prof_span(cvmx_t* h, int kind, int a, int b) {
 // the stager (`pageable`: the caller looked the source up once per call).
 inline cudaError_t h2d_copy(cvmx_t* h, void* dst, const void* src, size_t bytes, cudaStream_t stream, bool pageable) {
   if (pageable && h->use_stager && bytes >= ((size_t)4 << 20)) {
-    if (!h->stager) h->stager = new HostStager();
-    return h->stager->copy(dst, src, bytes, stream);
+    try {
+      if (!h->stager) h->stager = new HostStager();
+      return h->stager->copy(dst, src, bytes, stream);
+    } catch (...) {   // no worker threads to be had: leave this and later copies to the driver
+      h->use_stager = 0;
+    }
   }
   return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
@@ -202,12 +209,16 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 void plan_tiles(const cvmx_t* h, uint32_t want, std::vector<int2>& tiles) {
   tiles.clear();
   const int64_t TI = (h->K + GB - 1) / GB, TJ = (h->K + h->M + GB - 1) / GB;
-  for (int64_t bi = 0; bi < TI; ++bi)
-    for (int64_t bj = bi; bj < TJ; ++bj) {
-      const bool has_x = bj * GB < h->K;
-      const bool has_y = (bj + 1) * GB > h->K && h->M > 0;
-      if (((want & CVMX_WANT_XTX) && has_x) || ((want & CVMX_WANT_XTY) && has_y)) tiles.push_back(make_int2((int)bi, (int)bj));
-    }
+  // Diagonal tiles first: they issue 3/4 of the DMMAs of a full tile and, with fused fold statistics, every tile of a fold
+  // waits for their column chains before its epilogue - started first, they are done well before the others need them.
+  for (int pass = 0; pass < 2; ++pass)
+    for (int64_t bi = 0; bi < TI; ++bi)
+      for (int64_t bj = bi; bj < TJ; ++bj) {
+        if ((bi == bj) != (pass == 0)) continue;
+        const bool has_x = bj * GB < h->K;
+        const bool has_y = (bj + 1) * GB > h->K && h->M > 0;
+        if (((want & CVMX_WANT_XTX) && has_x) || ((want & CVMX_WANT_XTY) && has_y)) tiles.push_back(make_int2((int)bi, (int)bj));
+      }
 }
 
 // ---- row-split plan of few large folds -------------------------------------------------------------------------------
@@ -371,13 +382,21 @@ int32_t launch_k_gram(cvmx_t* h, unsigned grid, const GramParams<T>& gp) {
       return CVMX_OK;
     }
   }
+  if (gp.fuse_stats) {
+    if (!h->attr_gram_fused) {
+      CU(h, cudaFuncSetAttribute(k_gram<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes<T>()));
+      h->attr_gram_fused = true;
+    }
+    k_gram<T, true><<<grid, GLAUNCH, gram_smem_bytes<T>(), h->stream>>>(gp);
+    return CVMX_OK;
+  }
   k_gram<T><<<grid, GLAUNCH, gram_smem_bytes<T>(), h->stream>>>(gp);
   return CVMX_OK;
 }
 
 template <typename T>
 int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const EpiParams<T>& epi,
-                    cudaEvent_t stats_ready = nullptr) {
+                    cudaEvent_t stats_ready = nullptr, bool fuse_stats = false) {
   const int ntiles = (int)pl.tiles.size();
   if (ntiles == 0 || pl.units.empty()) return CVMX_OK;
   CU(h, h->units.reserve(pl.units.size() * sizeof(GramUnit)));
@@ -399,6 +418,20 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
   gp.partials = h->partials.as<double>();
   gp.raw_out = nullptr; gp.force_partials = 0;
   gp.epi = epi;
+  if (fuse_stats) {
+    const size_t nf = pl.fold_units.size();
+    CU(h, h->stat_flags.reserve(nf * sizeof(int)));
+    CU(h, cudaMemsetAsync(h->stat_flags.p, 0, nf * sizeof(int), h->stream));
+    int ndiag = 0;
+    for (const int2& t : pl.tiles) ndiag += t.x == t.y;
+    gp.fuse_stats = 1; gp.stat_flags = h->stat_flags.as<int>(); gp.stat_target = GPRODUCERS * ndiag;   // the producer warps of every diagonal tile
+    MomentParams<T>& mp = gp.mom;
+    mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = h->ld; mp.K = h->K; mp.M = h->M;
+    mp.offsets = d_indices; mp.indices = d_indices; mp.fold0 = 0; mp.N = h->N;   // offsets != nullptr: fold mode of finalize_column
+    mp.flags = h->flags; mp.resolution = (T)h->resolution;
+    mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+    mp.fs = epi.fs; mp.pw_cols = nullptr; mp.stats = const_cast<T*>(epi.stats); mp.raw = nullptr;
+  }
   const size_t smem = gram_smem_bytes<T>();
   if (!h->attr_gram) {
     CU(h, cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -600,7 +633,7 @@ int32_t join_stats(cvmx_t* h, cudaStream_t saved) {
 // concurrently - the chains store raw sums - and k_finalize_stats turns them into means / stds once both are done.
 template <typename T>
 int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, int64_t f0, int64_t Pn, int64_t max_rows,
-                          int col_shard, int n_col_shards, double overlap_ns, const T* have_raw = nullptr) {
+                          int col_shard, int n_col_shards, double overlap_ns, const T* have_raw = nullptr, bool masses_only = false) {
   const size_t sz = sizeof(T);
   const int64_t ld = h->ld;
   CU(h, h->fscal.reserve(Pn * sizeof(FoldScalars)));
@@ -636,6 +669,11 @@ int32_t launch_fold_stats(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx,
   }
   CU(h, cudaGetLastError());
   CU(h, cudaEventRecord(h->ev_mass, h->aux2_stream));
+  if (masses_only) {   // the column sums, means and stds are evaluated inside the Gram kernel (GramParams::fuse_stats)
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0));
+    prof_span(h, PROF_STATS, ev0, prof_mark(h));
+    return CVMX_OK;
+  }
   MomentParams<T> mp;
   mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
   mp.offsets = d_off; mp.indices = d_idx; mp.fold0 = f0; mp.N = h->N;
@@ -1258,6 +1296,10 @@ int32_t fit_end_impl(cvmx_t* h, int32_t col_shard, int32_t n_col_shards, const S
     }
     h->slab = true; h->N_glob = sl->N_glob; h->row0 = sl->row0;
   }
+  if (!sl && h->mass_started) {   // cvmx_slab_begin followed by a plain cvmx_fit_end: its weight mass ran over the global weights - redo
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_mass, 0));
+    h->mass_started = h->mass_pending = false;
+  }
   if (!h->fit_pre_done) { int32_t rp = fit_end_pre<T>(h, sl != nullptr, sl ? sl->N_glob : N); if (rp) return rp; }
   h->fit_pre_done = false;
   MomentParams<T> mp;
@@ -1322,6 +1364,12 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   }
   const bool want_mats = (want & (CVMX_WANT_XTX | CVMX_WANT_XTY)) != 0;
   const bool overlap = want_mats && h->flags != 0 && pl.split_folds.size() == (size_t)Pn;
+  const bool small = pl.max_rows <= SMALL_MAX_ROWS && K + M <= 4 * STHREADS;
+  // single-unit folds (the leave-many-out regime): the Gram kernel's diagonal tiles evaluate the column sums themselves -
+  // no second pass over the fold's rows.  Needs every diagonal tile (XTX wanted), no pairwise single-column sums, k_gram.
+  const bool fuse = want_mats && !small && h->fuse_stats && h->flags != 0 && (want & CVMX_WANT_XTX) && pl.split_folds.empty() &&
+                    K >= 2 && M != 1 && K + M <= round_up(K, GB) /* every column lies in a diagonal tile's block */ &&
+                    fmap_of<T>(h) == 0 && d_idx != nullptr;
   cudaStream_t main_stream = h->stream;
   if (overlap) {
     int32_t rc = fork_stats(h, &main_stream);
@@ -1330,7 +1378,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   {
     // device time the chains can hide behind: the Gram kernel when it overlaps them, nothing otherwise
     const double gram_ns = 2.0 * (double)(off[f1] - off[f0]) * (double)K * (double)(K + M) / 4e4;
-    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1, overlap ? gram_ns : 0.0);
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1, overlap ? gram_ns : 0.0, nullptr, fuse);
     if (rc) { h->stream = main_stream; return rc; }
   }
   if (overlap) {
@@ -1345,9 +1393,8 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     epi.out_xx = dxx; epi.xx_pitch = K; epi.xx_stride = K * K;
     epi.out_xy = dxy; epi.xy_pitch = M; epi.xy_stride = K * M;
     // the Gram kernel reads fold rows through absolute CSR positions
-    int32_t rc = (pl.max_rows <= SMALL_MAX_ROWS && K + M <= 4 * STHREADS)
-                     ? launch_small<T>(h, d_off, d_idx, off, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
-                     : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr);
+    int32_t rc = small ? launch_small<T>(h, d_off, d_idx, off, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
+                       : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr, fuse);
     if (rc) return rc;
   }
   return CVMX_OK;
@@ -1710,6 +1757,7 @@ int32_t cvmx_create(int32_t device, int32_t dtype, uint32_t flags, int64_t ddof,
   if (const char* e = std::getenv("CVMX_SCAN")) h->scan_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("CVMX_LOO_EXACT")) h->loo_mode = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_SCAN_SPEC")) h->scan_spec = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("CVMX_FUSE_STATS")) h->fuse_stats = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_HOST_STAGER")) h->use_stager = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("CVMX_F32_TC")) h->f32_tc = std::max(0, std::min(2, std::atoi(e)));
   DeviceGuard guard__(device);
@@ -1740,7 +1788,7 @@ int32_t cvmx_destroy(cvmx_t* h) {
   if (!h) return CVMX_OK;
   DeviceGuard guard__(h->device);
   cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->peer_sum, &h->w_glob, &h->g_off, &h->g_idx, &h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
+  for (DevBuf* b : {&h->stat_flags, &h->peer_sum, &h->w_glob, &h->g_off, &h->g_idx, &h->scan_look, &h->loo_ops, &h->Z, &h->w, &h->Ttot, &h->sum_z, &h->sumsq_z, &h->fit_scal, &h->d_off, &h->d_idx, &h->a_off, &h->a_idx,
                     &h->units, &h->tiles, &h->fold_units, &h->split_folds, &h->partials, &h->stats, &h->rawsums, &h->fscal, &h->pwcols,
                     &h->errflag, &h->out_xx, &h->out_xy, &h->out_small, &h->scan_seg, &h->scan_ok, &h->scan_list, &h->scan_cnt, &h->ystage, &h->fold_gram, &h->fold_raw, &h->chunk_ranges})
     b->release();
@@ -2298,8 +2346,13 @@ int64_t cvmx_partition_labels(const int64_t* labels, int64_t n, int64_t lo, int6
     nthreads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     if (const char* e = std::getenv("CVMX_PARTITION_THREADS")) nthreads = std::max(1, std::min(64, std::atoi(e)));
   }
-  if (nthreads == 1) return partition_labels_serial(labels, n, lo, span, scratch, first_rows, offsets, indices);
-  return partition_labels_threaded(labels, n, lo, span, scratch, first_rows, offsets, indices, nthreads);
+  if (nthreads > 1) {
+    try {
+      return partition_labels_threaded(labels, n, lo, span, scratch, first_rows, offsets, indices, nthreads);
+    } catch (...) {   // no threads / no memory for the per-thread histograms: the serial passes need neither
+    }
+  }
+  return partition_labels_serial(labels, n, lo, span, scratch, first_rows, offsets, indices);
 }
 
 int64_t cvmx_launch_count(const cvmx_t* h) { return h ? h->launches : 0; }

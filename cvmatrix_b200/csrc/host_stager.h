@@ -79,7 +79,11 @@ class HostStager {
       e = cudaEventCreateWithFlags(&done_[i], cudaEventDisableTiming);
       if (e != cudaSuccess) return e;
     }
-    for (int t = 1; t < nthreads_; ++t) workers_.emplace_back([this, t] { worker(t); });
+    try {
+      for (int t = 1; t < nthreads_; ++t) workers_.emplace_back([this, t] { worker(t); });
+    } catch (...) {
+      nthreads_ = (int)workers_.size() + 1;   // fewer threads than asked for: slices are cut for the ones that exist
+    }
     ready_ = true;
     return cudaSuccess;
   }

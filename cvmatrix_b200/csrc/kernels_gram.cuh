@@ -10,6 +10,7 @@
 // with each operation individually rounded in the model dtype, exactly as numpy evaluates it.
 #pragma once
 #include "common.cuh"
+#include "kernels_stats.cuh"
 
 namespace cvmx {
 
@@ -80,6 +81,16 @@ struct GramParams {
   // which kernel produced the accumulators, i.e. which (row, column) a thread's 64 values belong to
   //   0  k_gram<T>   (DMMA m8n8k4 fragments)      1  k_gram_tc   (float32 only: tensor-memory lanes, thread = output row)
   int fmap = 0;
+  // Fused fold statistics (k_gram, single-unit folds, XTX wanted): warps 4 / 5 of every diagonal-tile CTA - the warps that
+  // skip every other stage anyway - continue numpy's sequential column sums of the tile's 128 columns over the staged rows
+  // (sum w z, sum (w z) z: the chains of k_moments_pipe, without the extra pass over the fold's rows), turn them into the
+  // fold's mean / std (finalize_column; mom.stats == epi.stats, the fold scalars come from k_weight_mass before the
+  // launch) and signal stat_flags[fold]; every CTA of the fold waits for stat_target arrivals before its epilogue.
+  // The CTAs it waits for have block indices at most ntiles - 1 above its own, i.e. they are resident or done.
+  int fuse_stats = 0;
+  MomentParams<T> mom;
+  int* stat_flags = nullptr;
+  int stat_target = 0;
 };
 
 template <typename T>
@@ -265,8 +276,8 @@ __device__ __forceinline__ void gram_epilogue(double (&acc)[8][4][2], T* sC, con
 // the "empty" mbarrier; there is no block-wide barrier in the main loop and no compute warp ever issues a copy
 // (with the producer role on a compute warp the ~1300 issue cycles per stage sat on the critical path: ncu showed
 // 20 % of all samples in the full-barrier wait).  Row indices are fetched one stage ahead of their use.
-template <typename T>
-__global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
+template <typename T, bool FUSE = false>   // FUSE: fused fold statistics (GramParams::fuse_stats), a separate instantiation so that
+__global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {   // the plain kernel keeps its registers and schedule
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int PITCH = GramCfg<T>::PITCH;
   typedef typename GramCfg<T>::vec2 vec2;
@@ -288,8 +299,12 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
   const int64_t nrows = unit.row_end - unit.row_begin;
   const int64_t nk = (nrows + GBK - 1) / GBK;
 
+  const bool fused_epi = unit.nsplit == 1 && !p.force_partials;
+  // fused fold statistics: in a diagonal tile the four producer warps - idle between their copies - also CONSUME every stage:
+  // lane = one of the tile's 128 columns, continuing numpy's sequential column sums over the staged rows
+  const bool chain_tile = FUSE && diag && fused_epi;
   if (tid == 0) {
-    for (int s = 0; s < GSTAGES; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, GTHREADS / 32); }
+    for (int s = 0; s < GSTAGES; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, GTHREADS / 32 + (chain_tile ? GPRODUCERS : 0)); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -327,7 +342,44 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
 
   if (warp >= GTHREADS / 32) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GREGS_PRODUCER));
-    int64_t kt = warp - GTHREADS / 32;
+    const int pw = warp - GTHREADS / 32;
+    if (FUSE && chain_tile) {
+      // One loop over ALL stages: every producer warp adds stage j's rows to its 32 column chains, then the warp that owns
+      // stage j + GSTAGES - 1 refills the slot stage j - 1 left.  Chains: t = rn(w z), s += t, q += rn(t z), each op rounded, rows in the fold's order (kernels_stats.cuh).
+      static_assert(GSTAGES == GPRODUCERS, "one producer warp per ring slot");
+      int64_t mine = pw;                                    // next stage this warp issues
+      int64_t row = fetch_row(mine);
+      if (mine < nk) { const int64_t nr = fetch_row(mine + GPRODUCERS); issue(mine, row); row = nr; mine += GPRODUCERS; }
+      T cs = T(0), cq = T(0);
+      const int col = pw * 32 + lane;
+#pragma unroll 1
+      for (int64_t j = 0; j < nk; ++j) {
+        const int slot = (int)(j % GSTAGES);
+        mbar_wait(full + slot, (unsigned)(j / GSTAGES) & 1);
+        const T* zc = sA + (size_t)slot * GBK * PITCH + col;
+        const T* wb = sW + slot * GBK;
+        const int rows = (int)min((int64_t)GBK, nrows - j * GBK);
+#pragma unroll 4
+        for (int k = 0; k < rows; ++k) {
+          const T z = zc[k * PITCH];
+          const T t = Rn<T>::mul(z, wb[k]);
+          cs = Rn<T>::add(cs, t);
+          cq = Rn<T>::add(cq, Rn<T>::mul(t, z));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+        // refill the slot stage j - 1 left (chain first: its arrival is what the other eleven warps may be waiting for,
+        // the copy has three stages of slack)
+        if (mine == j + GSTAGES - 1 && mine < nk) { const int64_t nr = fetch_row(mine + GPRODUCERS); issue(mine, row); row = nr; mine += GPRODUCERS; }
+      }
+      finalize_column<T>(p.mom, unit.fold, (int64_t)bi * GB + col, cs, cq);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(p.stat_flags + unit.fold, 1);
+      cp_async_wait<0>();
+      return;
+    }
+    int64_t kt = pw;
     int64_t row = fetch_row(kt);
 #pragma unroll 1
     for (; kt < nk; kt += GPRODUCERS) {
@@ -419,6 +471,18 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + slot);
   }
+  if (FUSE && fused_epi) {
+    // The fold's mean / std rows are complete once the producer warps of every diagonal tile have signalled - and in a
+    // diagonal tile this is also what says that ITS producer warps have read the last stages: the ring must not be reused
+    // (split-K merge, epilogue tile) before that.
+    if (tid == 0) {
+      int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(p.stat_flags + unit.fold) : "memory");
+        if (seen < p.stat_target) __nanosleep(64);
+      } while (seen < p.stat_target);
+    }
+  }
   compute_barrier();   // every stage consumed by every compute warp: the ring can be reused as the epilogue tile
 
   if (diag) {
@@ -449,7 +513,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {
     compute_barrier();
   }
 
-  if (unit.nsplit == 1 && !p.force_partials) {
+  if (fused_epi) {
     gram_epilogue<T>(acc, reinterpret_cast<T*>(smem_raw), p.epi, unit.fold, bi, bj);
   } else {
     double* dst = p.partials + ((size_t)(unit.part_base + unit.split) * p.ntiles + tile) * (size_t)(GACC * GTHREADS);
