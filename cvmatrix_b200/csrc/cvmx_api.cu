@@ -329,7 +329,9 @@ void plan_units(const cvmx_t* h, const int64_t* off, int64_t f0, int64_t f1, int
   if (rows_per_unit != INT64_MAX && ntiles < sms) {     // (wide K: the tiles alone fill the GPU - equal, long units)
     std::vector<int64_t> fold_rows;
     for (int64_t f = f0; f < f1; ++f) fold_rows.push_back(off[f + 1] - off[f]);
-    tapered = plan_tapered(fold_rows, pl.tiles, sms, 1024, 8192);
+    int64_t r_hi = 8192;
+    if (const char* e = std::getenv("CVMX_PLAN_RHI")) r_hi = std::max<int64_t>(1024, std::atoll(e));   // experiment knob
+    tapered = plan_tapered(fold_rows, pl.tiles, sms, 1024, r_hi);
   }
   for (int64_t f = f0; f < f1; ++f) {
     const int64_t beg = off[f], n = off[f + 1] - off[f];

@@ -24,4 +24,13 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 for c in cfg2 cfg3 cfg4; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_$c.csv python bench.py --config $c --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-also > /dev/null 2>&1
 done
-ls -la gpurun_out | tail -24
+# DRAM traffic of the dominant kernel per step (roofline.traffic): ncu --set full over the timed steps only
+NCUT="ncu --set full --clock-control none --profile-from-start off -f"
+B="python bench.py --steps 1 --no-e2e --no-cpu-baseline --no-also --no-parity"
+BENCH_CUDA_PROFILER=1 timeout 400 $NCUT -k regex:^k_gram -c 1 -o gpurun_out/${TAG}_traffic_cfg2 $B --config cfg2 > /dev/null 2>&1
+BENCH_CUDA_PROFILER=1 timeout 400 $NCUT -k regex:^k_gram -c 1 -o gpurun_out/${TAG}_traffic_cfg3 $B --config cfg3 > /dev/null 2>&1
+BENCH_CUDA_PROFILER=1 timeout 400 $NCUT -k regex:^k_loo -c 10 -o gpurun_out/${TAG}_traffic_cfg4 $B --config cfg4 > /dev/null 2>&1
+BENCH_CUDA_PROFILER=1 BENCH_EMULATE_SHARDS=8 timeout 400 $NCUT -k regex:^k_gram -c 1 -o gpurun_out/${TAG}_traffic_cfg2_s8 $B --config cfg2 > /dev/null 2>&1
+BENCH_CUDA_PROFILER=1 BENCH_EMULATE_SHARDS=2 timeout 400 $NCUT -k regex:^k_gram -c 1 -o gpurun_out/${TAG}_traffic_cfg2_s2 $B --config cfg2 > /dev/null 2>&1
+BENCH_CUDA_PROFILER=1 BENCH_EMULATE_SHARDS=4 timeout 400 $NCUT -k regex:^k_gram -c 1 -o gpurun_out/${TAG}_traffic_cfg2_s4 $B --config cfg2 > /dev/null 2>&1
+ls -la gpurun_out | tail -30
