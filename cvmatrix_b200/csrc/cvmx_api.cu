@@ -2283,33 +2283,35 @@ static int64_t partition_labels_serial(const int64_t* labels, int64_t n, int64_t
 // stable, and needs no atomics.  Same result as the serial form, element for element.
 static int64_t partition_labels_threaded(const int64_t* labels, int64_t n, int64_t lo, int64_t span, int64_t* scratch, int64_t* first_rows,
                                          int64_t* offsets, int64_t* indices, int nthreads) {
-  std::vector<int64_t> hist((size_t)nthreads * span, 0), first((size_t)nthreads * span, -1);
-  std::vector<int> bad((size_t)nthreads, 0);
+  // per-thread tables padded to whole cache lines: with five labels all threads' counters would otherwise share one line
+  const size_t stride = ((size_t)span + 7) / 8 * 8 + 8;
+  std::vector<int64_t> hist((size_t)nthreads * stride, 0), first((size_t)nthreads * stride, -1);
+  std::vector<int> bad((size_t)nthreads * 16, 0);
   auto chunk = [&](int t) { return std::make_pair(n * t / nthreads, n * (t + 1) / nthreads); };
   {
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t)
       th.emplace_back([&, t] {
-        int64_t* h = hist.data() + (size_t)t * span;
-        int64_t* f = first.data() + (size_t)t * span;
+        int64_t* h = hist.data() + (size_t)t * stride;
+        int64_t* f = first.data() + (size_t)t * stride;
         const auto [b, e] = chunk(t);
         for (int64_t i = b; i < e; ++i) {
           const int64_t l = labels[i] - lo;
-          if (l < 0 || l >= span) { bad[t] = 1; return; }
+          if (l < 0 || l >= span) { bad[(size_t)t * 16] = 1; return; }
           if (h[l]++ == 0) f[l] = i;
         }
       });
     for (auto& x : th) x.join();
   }
-  for (int t = 0; t < nthreads; ++t) if (bad[t]) return -1;
+  for (int t = 0; t < nthreads; ++t) if (bad[(size_t)t * 16]) return -1;
   int64_t* slot = scratch;          // label -> fold position (-1: unseen)
   int64_t* count = scratch + span;  // label -> number of rows
   std::vector<std::pair<int64_t, int64_t>> seen;   // (first row, label)
   for (int64_t l = 0; l < span; ++l) {
     int64_t fr = -1, c = 0;
     for (int t = 0; t < nthreads; ++t) {
-      c += hist[(size_t)t * span + l];
-      if (fr < 0) fr = first[(size_t)t * span + l];   // chunks are in row order: the first chunk that saw the label
+      c += hist[(size_t)t * stride + l];
+      if (fr < 0) fr = first[(size_t)t * stride + l];   // chunks are in row order: the first chunk that saw the label
     }
     slot[l] = -1; count[l] = c;
     if (c > 0) seen.emplace_back(fr, l);
@@ -2325,13 +2327,13 @@ static int64_t partition_labels_threaded(const int64_t* labels, int64_t n, int64
   for (int64_t l = 0; l < span; ++l) {
     if (slot[l] < 0) continue;
     int64_t pos = offsets[slot[l]];
-    for (int t = 0; t < nthreads; ++t) { const int64_t c = hist[(size_t)t * span + l]; hist[(size_t)t * span + l] = pos; pos += c; }
+    for (int t = 0; t < nthreads; ++t) { const int64_t c = hist[(size_t)t * stride + l]; hist[(size_t)t * stride + l] = pos; pos += c; }
   }
   {
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t)
       th.emplace_back([&, t] {
-        int64_t* pos = hist.data() + (size_t)t * span;
+        int64_t* pos = hist.data() + (size_t)t * stride;
         const auto [b, e] = chunk(t);
         for (int64_t i = b; i < e; ++i) indices[pos[labels[i] - lo]++] = i;
       });
