@@ -81,12 +81,13 @@ struct GramParams {
   // which kernel produced the accumulators, i.e. which (row, column) a thread's 64 values belong to
   //   0  k_gram<T>   (DMMA m8n8k4 fragments)      1  k_gram_tc   (float32 only: tensor-memory lanes, thread = output row)
   int fmap = 0;
-  // Fused fold statistics (k_gram, single-unit folds, XTX wanted): warps 4 / 5 of every diagonal-tile CTA - the warps that
-  // skip every other stage anyway - continue numpy's sequential column sums of the tile's 128 columns over the staged rows
-  // (sum w z, sum (w z) z: the chains of k_moments_pipe, without the extra pass over the fold's rows), turn them into the
-  // fold's mean / std (finalize_column; mom.stats == epi.stats, the fold scalars come from k_weight_mass before the
-  // launch) and signal stat_flags[fold]; every CTA of the fold waits for stat_target arrivals before its epilogue.
-  // The CTAs it waits for have block indices at most ntiles - 1 above its own, i.e. they are resident or done.
+  // Fused fold statistics (k_gram<T, true>; single-unit folds, XTX wanted): in every diagonal-tile CTA the four producer
+  // warps - idle between their copies - also consume every stage and continue numpy's sequential column sums of the
+  // tile's 128 columns over the staged rows (sum w z, sum (w z) z: the chains of k_moments_pipe without the extra pass
+  // over the fold's rows), turn them into the fold's mean / std (finalize_column; mom.stats == epi.stats, the fold
+  // scalars come from k_weight_mass before the launch) and signal stat_flags[fold]; every CTA of the fold waits for
+  // stat_target arrivals after its main loop.  Tiles are ordered diagonal-first inside a fold, and the CTAs a CTA waits
+  // for have block indices below its own or at most ntiles - 1 above, i.e. they are resident or done.
   int fuse_stats = 0;
   MomentParams<T> mom;
   int* stat_flags = nullptr;
