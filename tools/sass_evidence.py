@@ -1,5 +1,6 @@
-"""Opcode evidence from the built library (no GPU needed): cuobjdump -sass cvmatrix_b200/libcvmx.so -> profiles/r01_sass_evidence.txt
-(DMMA = FP64 tensor cores, UBLKCP = TMA bulk copy, SYNCS = mbarrier, LDGSTS = cp.async, USETMAXREG = setmaxnreg)."""
+"""Opcode evidence from the built library (no GPU needed): cuobjdump -sass cvmatrix_b200/libcvmx.so -> profiles/r02_sass_evidence.txt
+(DMMA = FP64 tensor cores, UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = TMA bulk copy, SYNCS = mbarrier,
+LDGSTS = cp.async, USETMAXREG = setmaxnreg)."""
 import collections
 import os
 import re
@@ -20,8 +21,8 @@ for line in out.splitlines():
         per[cur][m.group(1)] += 1
 names = subprocess.run(["c++filt"] + list(per.keys()), capture_output=True, text=True).stdout.splitlines()
 keys = ["DMMA.8x8x4", "DFMA", "DMUL", "DADD", "MUFU.RCP64H", "UBLKCP.S.G", "USETMAXREG.TRY_ALLOC.CTAPOOL", "USETMAXREG.DEALLOC.CTAPOOL"]
-keys += sorted(k for k in counts if k.split(".")[0] in ("LDGSTS", "SYNCS", "ARRIVES", "SHFL"))
-with open(os.path.join(ROOT, "profiles", "r01_sass_evidence.txt"), "w") as f:
+keys += sorted(k for k in counts if k.split(".")[0] in ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UTMALDG", "LDGSTS", "SYNCS", "ARRIVES", "SHFL"))
+with open(os.path.join(ROOT, "profiles", "r02_sass_evidence.txt"), "w") as f:
     f.write("# SASS evidence (cuobjdump -sass cvmatrix_b200/libcvmx.so, sm_100a only; regenerate: python tools/sass_evidence.py)\n\n")
     f.write("## opcode counts over the whole library\n")
     for k in keys:
@@ -32,10 +33,11 @@ with open(os.path.join(ROOT, "profiles", "r01_sass_evidence.txt"), "w") as f:
     seen = set()
     for name, c in zip(names, per.values()):
         short = re.sub(r"k_loo_folds<(\w+), \d+>", r"k_loo_folds<\1, *>", name)
-        if "float" in short or short in seen:
+        if ("float" in short and "k_gram_tc" not in short) or short in seen:
             continue
         seen.add(short)
         g = lambda p: sum(v for o, v in c.items() if o.startswith(p))  # noqa: E731
-        f.write(f"{short[:90]} | DMMA {g('DMMA')} | UBLKCP {g('UBLKCP')} | SYNCS {g('SYNCS')} | LDGSTS {g('LDGSTS')} | DADD {c['DADD']} | "
+        tc = f" | UTCHMMA {g('UTCHMMA')} | LDTM {g('LDTM')} | UTCBAR {g('UTCBAR')}" if g("UTCHMMA") else ""
+        f.write(f"{short[:90]}{tc} | DMMA {g('DMMA')} | UBLKCP {g('UBLKCP')} | SYNCS {g('SYNCS')} | LDGSTS {g('LDGSTS')} | DADD {c['DADD']} | "
                 f"DMUL {c['DMUL']} | DFMA {c['DFMA']} | SHFL {g('SHFL')}\n")
-print(open(os.path.join(ROOT, "profiles", "r01_sass_evidence.txt")).read())
+print(open(os.path.join(ROOT, "profiles", "r02_sass_evidence.txt")).read())
