@@ -467,7 +467,7 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
 // Small folds (every fold of the batch has <= SMALL_MAX_ROWS rows): streaming rank-n kernel, no tensor cores.
 template <typename T>
 int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const int64_t* off, int64_t f0, int64_t Pn, uint32_t want,
-                     const EpiParams<T>& epi, cudaEvent_t stats_ready) {
+                     const EpiParams<T>& epi, cudaEvent_t stats_ready, bool loo_stats = false) {
   if (stats_ready) CU(h, cudaStreamWaitEvent(h->stream, stats_ready, 0));
   SmallParams<T> sp;
   sp.Z = h->Z.as<T>(); sp.w = h->w.as<T>(); sp.ld = h->ld;
@@ -495,8 +495,19 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
       // streaming form: operand rows of every fold, then 32 x 128 output tiles streamed over the folds
       const int64_t pos0 = off[f0 + c0], ld = h->ld;
       CU(h, h->loo_ops.reserve((size_t)nf * 4 * ld * sizeof(double)));
-      k_loo_operands<T><<<dim3((unsigned)nf, (unsigned)((ld + 127) / 128)), 128, 0, h->stream>>>(
-          h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<double>());
+      if (loo_stats) {   // one-row folds: means / stds inside the operand kernel (no separate statistics pass ran)
+        MomentParams<T> mp;
+        mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = ld; mp.K = h->K; mp.M = h->M;
+        mp.offsets = d_off; mp.indices = d_idx; mp.fold0 = 0; mp.N = h->N;   // offsets != nullptr: fold mode of finalize_column
+        mp.flags = h->flags; mp.resolution = (T)h->resolution;
+        mp.sum_z = h->sum_z.as<T>(); mp.sumsq_z = h->sumsq_z.as<T>();
+        mp.fs = q.epi.fs; mp.pw_cols = nullptr; mp.stats = const_cast<T*>(q.epi.stats); mp.raw = nullptr;
+        k_loo_operands<T, true><<<dim3((unsigned)nf, (unsigned)((ld + 127) / 128)), 128, 0, h->stream>>>(
+            h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<double>(), mp);
+      } else {
+        k_loo_operands<T><<<dim3((unsigned)nf, (unsigned)((ld + 127) / 128)), 128, 0, h->stream>>>(
+            h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, d_idx + pos0, q.epi.stats, q.epi.fs, h->flags & 15u, h->loo_ops.as<double>());
+      }
       const int col_tiles = (int)((h->K + h->M + LOO_TC - 1) / LOO_TC), row_tiles = (int)((h->K + LOO_TR - 1) / LOO_TR);
       k_loo_tiles<T><<<dim3((unsigned)(col_tiles * row_tiles), (unsigned)((nf + LOO_FOLDS - 1) / LOO_FOLDS)), LOO_THREADS, 0, h->stream>>>(
           h->Ttot.as<T>(), h->loo_ops.as<double>(), ld, h->K, h->M, col_tiles, nf, want, q.epi.out_xx, q.epi.xx_pitch, q.epi.xx_stride,
@@ -1369,6 +1380,9 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   const bool small = pl.max_rows <= SMALL_MAX_ROWS && K + M <= 4 * STHREADS;
   // single-unit folds (the leave-many-out regime): the Gram kernel's diagonal tiles evaluate the column sums themselves -
   // no second pass over the fold's rows.  Needs every diagonal tile (XTX wanted), no pairwise single-column sums, k_gram.
+  // leave-one-out in the streaming form: the operand kernel forms the means / stds of its one-row folds itself
+  bool all_one = small && h->loo_mode == 0 && h->fuse_stats && h->flags != 0 && want_mats && K >= 2 && M != 1 && Pn <= (int64_t)65535 * SMALL_FOLDS;
+  for (int64_t f = f0; f < f1 && all_one; ++f) all_one = off[f + 1] - off[f] == 1;
   const bool fuse = want_mats && !small && h->fuse_stats && h->flags != 0 && (want & CVMX_WANT_XTX) && pl.split_folds.empty() &&
                     K >= 2 && M != 1 && K + M <= round_up(K, GB) /* every column lies in a diagonal tile's block */ &&
                     fmap_of<T>(h) == 0 && d_idx != nullptr;
@@ -1380,7 +1394,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   {
     // device time the chains can hide behind: the Gram kernel when it overlaps them, nothing otherwise
     const double gram_ns = 2.0 * (double)(off[f1] - off[f0]) * (double)K * (double)(K + M) / 4e4;
-    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1, overlap ? gram_ns : 0.0, nullptr, fuse);
+    int32_t rc = launch_fold_stats<T>(h, d_off, d_idx, f0, Pn, pl.max_rows, 0, 1, overlap ? gram_ns : 0.0, nullptr, fuse || all_one);
     if (rc) { h->stream = main_stream; return rc; }
   }
   if (overlap) {
@@ -1395,7 +1409,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
     epi.out_xx = dxx; epi.xx_pitch = K; epi.xx_stride = K * K;
     epi.out_xy = dxy; epi.xy_pitch = M; epi.xy_stride = K * M;
     // the Gram kernel reads fold rows through absolute CSR positions
-    int32_t rc = small ? launch_small<T>(h, d_off, d_idx, off, f0, Pn, want, epi, overlap ? h->ev_join : nullptr)
+    int32_t rc = small ? launch_small<T>(h, d_off, d_idx, off, f0, Pn, want, epi, overlap ? h->ev_join : nullptr, all_one)
                        : launch_gram<T>(h, pl, d_idx, epi, overlap ? h->ev_join : nullptr, fuse);
     if (rc) return rc;
   }

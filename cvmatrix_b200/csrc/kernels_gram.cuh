@@ -917,10 +917,14 @@ constexpr int LOO_TR = 32, LOO_TC = 128, LOO_FOLDS = 32, LOO_THREADS = 256;
 
 // operand rows are float64 for both model dtypes: a float32 model then rounds ONCE, on the final store (its own
 // float32 evaluation of T - G loses ~1e-5 of the centred result to cancellation)
-template <typename T>
+// STATS: the fold's column sums are the row itself (s = rn(w z), q = rn(s z): numpy's sequential sum of one row), so the
+// thread also turns them into the fold's mean / std (finalize_column, into mom.stats == stats) instead of reading the
+// output of a separate statistics pass; the fold scalars still come from k_weight_mass.
+template <typename T, bool STATS = false>
 __global__ void __launch_bounds__(128) k_loo_operands(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t K, int64_t M,
                                                       const int64_t* __restrict__ rows, const T* __restrict__ stats,
-                                                      const FoldScalars* __restrict__ fs, uint32_t flags, double* __restrict__ opnd) {
+                                                      const FoldScalars* __restrict__ fs, uint32_t flags, double* __restrict__ opnd,
+                                                      const MomentParams<T> mom = MomentParams<T>()) {
   const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   const int64_t f = blockIdx.x;
   if (c >= ld) return;
@@ -929,7 +933,14 @@ __global__ void __launch_bounds__(128) k_loo_operands(const T* __restrict__ Z, c
   const bool cX = flags & 1, cY = flags & 2, sX = flags & 4, sY = flags & 8;
   const bool isX = c < K;
   const int64_t row = rows[f];
-  const double mean = (double)stats[(size_t)f * 2 * ld + c], sd = (double)stats[(size_t)f * 2 * ld + ld + c];
+  if (STATS) {
+    const T z = Z[row * ld + c];
+    const T wz = Rn<T>::mul(z, w[row]);
+    finalize_column<T>(mom, f, c, Rn<T>::add(T(0), wz), Rn<T>::add(T(0), Rn<T>::mul(wz, z)));
+  }
+  // (STATS: read back through the pointer just written - `stats` is a restrict-qualified read-only view of the same rows)
+  const T* st = STATS ? mom.stats : stats;
+  const double mean = (double)st[(size_t)f * 2 * ld + c], sd = (double)st[(size_t)f * 2 * ld + ld + c];
   const double rsw = __dsqrt_rn(fs[f].sw);
   o[c] = __dmul_rn(__dsqrt_rn((double)w[row]), (double)Z[row * ld + c]);
   const double um = __dmul_rn(rsw, mean);
