@@ -209,12 +209,14 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 void plan_tiles(const cvmx_t* h, uint32_t want, std::vector<int2>& tiles) {
   tiles.clear();
   const int64_t TI = (h->K + GB - 1) / GB, TJ = (h->K + h->M + GB - 1) / GB;
-  // Diagonal tiles first: they issue 3/4 of the DMMAs of a full tile and, with fused fold statistics, every tile of a fold
-  // waits for their column chains before its epilogue - started first, they are done well before the others need them.
+  // Diagonal tiles first (and the tiles (0, bj >= TI) of Y-only column blocks): with fused fold statistics every tile of a
+  // fold waits for their column chains before its epilogue - started first, and the diagonal ones issuing 3/4 of the DMMAs
+  // of a full tile, they are done before the others need them.
   for (int pass = 0; pass < 2; ++pass)
     for (int64_t bi = 0; bi < TI; ++bi)
       for (int64_t bj = bi; bj < TJ; ++bj) {
-        if ((bi == bj) != (pass == 0)) continue;
+        const bool first = bi == bj || (bi == 0 && bj >= TI);   // the tiles that carry column chains (GramParams::fuse_stats)
+        if (first != (pass == 0)) continue;
         const bool has_x = bj * GB < h->K;
         const bool has_y = (bj + 1) * GB > h->K && h->M > 0;
         if (((want & CVMX_WANT_XTX) && has_x) || ((want & CVMX_WANT_XTY) && has_y)) tiles.push_back(make_int2((int)bi, (int)bj));
@@ -424,9 +426,10 @@ int32_t launch_gram(cvmx_t* h, const Plan& pl, const int64_t* d_indices, const E
     const size_t nf = pl.fold_units.size();
     CU(h, h->stat_flags.reserve(nf * sizeof(int)));
     CU(h, cudaMemsetAsync(h->stat_flags.p, 0, nf * sizeof(int), h->stream));
-    int ndiag = 0;
-    for (const int2& t : pl.tiles) ndiag += t.x == t.y;
-    gp.fuse_stats = 1; gp.stat_flags = h->stat_flags.as<int>(); gp.stat_target = GPRODUCERS * ndiag;   // the producer warps of every diagonal tile
+    const int TI = (int)((h->K + GB - 1) / GB);
+    int nchain = 0;
+    for (const int2& t : pl.tiles) nchain += t.x == t.y || (t.x == 0 && t.y >= TI);
+    gp.fuse_stats = 1; gp.stat_flags = h->stat_flags.as<int>(); gp.stat_target = GPRODUCERS * nchain;   // the producer warps of every chain tile
     MomentParams<T>& mp = gp.mom;
     mp.Z = h->Z.as<T>(); mp.w = h->w.as<T>(); mp.ld = h->ld; mp.K = h->K; mp.M = h->M;
     mp.offsets = d_indices; mp.indices = d_indices; mp.fold0 = 0; mp.N = h->N;   // offsets != nullptr: fold mode of finalize_column
@@ -1384,7 +1387,7 @@ int32_t run_folds(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, const i
   bool all_one = small && h->loo_mode == 0 && h->fuse_stats && h->flags != 0 && want_mats && K >= 2 && M != 1 && Pn <= (int64_t)65535 * SMALL_FOLDS;
   for (int64_t f = f0; f < f1 && all_one; ++f) all_one = off[f + 1] - off[f] == 1;
   const bool fuse = want_mats && !small && h->fuse_stats && h->flags != 0 && (want & CVMX_WANT_XTX) && pl.split_folds.empty() &&
-                    K >= 2 && M != 1 && K + M <= round_up(K, GB) /* every column lies in a diagonal tile's block */ &&
+                    K >= 2 && M != 1 && (K + M <= round_up(K, GB) || (want & CVMX_WANT_XTY)) /* every column block has a chain tile */ &&
                     fmap_of<T>(h) == 0 && d_idx != nullptr;
   cudaStream_t main_stream = h->stream;
   if (overlap) {

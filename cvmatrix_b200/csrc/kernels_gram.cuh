@@ -86,8 +86,9 @@ struct GramParams {
   // tile's 128 columns over the staged rows (sum w z, sum (w z) z: the chains of k_moments_pipe without the extra pass
   // over the fold's rows), turn them into the fold's mean / std (finalize_column; mom.stats == epi.stats, the fold
   // scalars come from k_weight_mass before the launch) and signal stat_flags[fold]; every CTA of the fold waits for
-  // stat_target arrivals after its main loop.  Tiles are ordered diagonal-first inside a fold, and the CTAs a CTA waits
-  // for have block indices below its own or at most ntiles - 1 above, i.e. they are resident or done.
+  // stat_target arrivals after its main loop.  Column blocks past the last diagonal block (Y columns beyond round_up(K, 128))
+  // are chained by the tile (0, bj) from its B operand.  Tiles are ordered chain-tiles-first inside a fold, and the CTAs a
+  // CTA waits for have block indices below its own or at most ntiles - 1 above, i.e. they are resident or done.
   int fuse_stats = 0;
   MomentParams<T> mom;
   int* stat_flags = nullptr;
@@ -302,8 +303,9 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {   
 
   const bool fused_epi = unit.nsplit == 1 && !p.force_partials;
   // fused fold statistics: in a diagonal tile the four producer warps - idle between their copies - also CONSUME every stage:
-  // lane = one of the tile's 128 columns, continuing numpy's sequential column sums over the staged rows
-  const bool chain_tile = FUSE && diag && fused_epi;
+  // lane = one of the 128 columns of the tile's column block, continuing numpy's sequential column sums over the staged rows
+  // (column blocks past the last diagonal block - Y columns when K + M > round_up(K, 128) - belong to the tile (0, bj))
+  const bool chain_tile = FUSE && fused_epi && (diag || (bi == 0 && bj >= (int)((p.epi.K + GB - 1) / GB)));
   if (tid == 0) {
     for (int s = 0; s < GSTAGES; ++s) { mbar_init(full + s, 33); mbar_init(empty + s, GTHREADS / 32 + (chain_tile ? GPRODUCERS : 0)); }
     mbar_fence_init();
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {   
       for (int64_t j = 0; j < nk; ++j) {
         const int slot = (int)(j % GSTAGES);
         mbar_wait(full + slot, (unsigned)(j / GSTAGES) & 1);
-        const T* zc = sA + (size_t)slot * GBK * PITCH + col;
+        const T* zc = (diag ? sA : sB) + (size_t)slot * GBK * PITCH + col;
         const T* wb = sW + slot * GBK;
         const int rows = (int)min((int64_t)GBK, nrows - j * GBK);
 #pragma unroll 4
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(GLAUNCH, 1) k_gram(const GramParams<T> p) {   
         // the copy has three stages of slack)
         if (mine == j + GSTAGES - 1 && mine < nk) { const int64_t nr = fetch_row(mine + GPRODUCERS); issue(mine, row); row = nr; mine += GPRODUCERS; }
       }
-      finalize_column<T>(p.mom, unit.fold, (int64_t)bi * GB + col, cs, cq);
+      finalize_column<T>(p.mom, unit.fold, (int64_t)bj * GB + col, cs, cq);
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(p.stat_flags + unit.fold, 1);

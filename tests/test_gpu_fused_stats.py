@@ -36,7 +36,9 @@ CASES = [
     (6000, 300, 7, 40, np.float64, True),     # 3 diagonal tiles, K and K + M not multiples of 128, 150-row folds (tail stage)
     (5000, 100, 0, 25, np.float64, True),     # one tile, no Y
     (4000, 130, 5, 16, np.float64, False),    # unweighted, a 2-column last tile row
-    (3000, 256, 6, 10, np.float64, True),     # K a multiple of 128: Y lies outside every diagonal block -> separate pass either way
+    (3000, 256, 6, 10, np.float64, True),     # K a multiple of 128: the Y columns are chained by the tile (0, 2) from its B operand
+    (3000, 500, 20, 8, np.float64, True),     # Y straddles the last diagonal block (500..511) and a Y-only block (512..519)
+    (2000, 128, 3, 8, np.float64, True),      # one diagonal tile + one Y-only tile
     (3000, 250, 6, 10, np.float32, True),     # float32 model on the DMMA kernel
     (2400, 60, 3, 2400 // 17, np.float64, True),   # 17-row folds: one full stage + one row
 ]
