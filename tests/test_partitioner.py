@@ -56,3 +56,28 @@ def test_special_labels():
         Partitioner([1, 2]).get_validation_indices("nope")
     with pytest.raises(TypeError):
         Partitioner(np.zeros((3, 2)))  # rows are unhashable, as in the reference
+
+
+def test_native_partition_thread_counts_agree(monkeypatch):
+    """The threaded counting passes (cvmx_partition_labels, long arrays with few labels) give the serial result for every
+    thread count - offsets, indices, key order - including labels that first appear late and negative labels."""
+    import numpy as np
+
+    from cvmatrix_b200 import Partitioner
+
+    rng = np.random.default_rng(3)
+    N = 250_000
+    cases = [np.arange(N) % 5, rng.integers(-3, 40, size=N), np.where(np.arange(N) < N - 7, np.arange(N) % 3, 1000 + np.arange(N) % 2)]
+    for labels in cases:
+        monkeypatch.setenv("CVMX_PARTITION_THREADS", "1")
+        ref = Partitioner(labels)
+        for nt in ("2", "3", "8", "13"):
+            monkeypatch.setenv("CVMX_PARTITION_THREADS", nt)
+            p = Partitioner(labels)
+            assert [int(k) for k in p.folds_dict] == [int(k) for k in ref.folds_dict]
+            assert np.array_equal(p.offsets, ref.offsets) and np.array_equal(p.indices, ref.indices)
+        # against the definition
+        first_seen = list(dict.fromkeys(labels.tolist()))
+        assert [int(k) for k in ref.folds_dict] == first_seen
+        for k in first_seen[:3]:
+            assert np.array_equal(ref.get_validation_indices(k), np.flatnonzero(labels == k))

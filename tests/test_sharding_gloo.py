@@ -131,3 +131,31 @@ def test_weighted_slab_bounds():
     assert sharding.weighted_slab_bounds([0, 0, 0], 50) == [0, 16, 32, 50]           # no rates: equal slabs
     assert sharding.weighted_slab_bounds([1, 0, 1, 5], 64) == [0, 16, 32, 48, 64]    # every rank keeps a block
     assert sharding.weighted_slab_bounds([3.0], 10) == [0, 10]
+
+
+def test_local_csr_paths_agree():
+    """Few folds (per-fold binary search) and many folds (one vectorised pass) give the same local CSR; unsorted folds are
+    refused unless the caller vouches for them."""
+    import numpy as np
+    import pytest
+
+    from cvmatrix_b200 import sharding
+
+    rng = np.random.default_rng(5)
+    N = 20_000
+    for P in (3, 5000):
+        labels = rng.integers(0, P, size=N)
+        order = np.argsort(labels, kind="stable").astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=P))]).astype(np.int64)
+        for r0, r1 in ((0, N), (3000, 9000), (N - 1, N), (500, 500)):
+            loc, idx = sharding.local_csr(offsets, order, r0, r1)
+            loc2, idx2 = sharding.local_csr(offsets, order, r0, r1, assume_sorted=True)
+            assert np.array_equal(loc, loc2) and np.array_equal(idx, idx2)
+            want = [order[offsets[f]:offsets[f + 1]] for f in range(P)]
+            want = [v[(v >= r0) & (v < r1)] - r0 for v in want]
+            assert np.array_equal(idx, np.concatenate(want)) and np.array_equal(np.diff(loc), [v.size for v in want])
+    with pytest.raises(ValueError, match="fold 1"):
+        sharding.local_csr(np.array([0, 2, 5]), np.array([0, 4, 3, 2, 9]), 0, 10)
+    # a step down exactly at a fold boundary is fine
+    loc, idx = sharding.local_csr(np.array([0, 2, 4]), np.array([5, 9, 0, 3]), 2, 8)
+    assert loc.tolist() == [0, 1, 2] and idx.tolist() == [3, 1]
