@@ -525,6 +525,28 @@ int32_t launch_small(cvmx_t* h, const int64_t* d_off, const int64_t* d_idx, cons
         CVMX_LOO_CASE(13) CVMX_LOO_CASE(14) CVMX_LOO_CASE(15)
 #undef CVMX_LOO_CASE
       }
+    } else if (h->loo_mode == 0) {
+      // leave-few-out, streaming form: operand rows of every fold (bounded workspace: sub-batches), then the tile kernel
+      const int64_t ld = h->ld;
+      int R = 1;
+      for (int64_t f = f0 + c0; f < f0 + c0 + nf; ++f) R = (int)std::max<int64_t>(R, off[f + 1] - off[f]);
+      const size_t per_fold = (size_t)(3 + R) * ld * sizeof(double);
+      const int64_t sub = std::max<int64_t>(LOO_FOLDS, (int64_t)(((size_t)512 << 20) / per_fold) / LOO_FOLDS * LOO_FOLDS);
+      const int col_tiles = (int)((h->K + h->M + LOO_TC - 1) / LOO_TC), row_tiles = (int)((h->K + LOO_TR - 1) / LOO_TR);
+      for (int64_t s0 = 0; s0 < nf; s0 += sub) {
+        const int64_t ns = std::min(sub, nf - s0);
+        CU(h, h->loo_ops.reserve((size_t)ns * per_fold));
+        const int64_t* offs = d_off + f0 + c0 + s0;
+        k_few_operands<T><<<dim3((unsigned)ns, (unsigned)((ld + 127) / 128)), 128, 0, h->stream>>>(
+            h->Z.as<T>(), h->w.as<T>(), ld, h->K, h->M, offs, d_idx, q.epi.stats + (size_t)s0 * 2 * ld, q.epi.fs + s0, h->flags & 15u, R,
+            h->loo_ops.as<double>());
+        k_few_tiles<T><<<dim3((unsigned)(col_tiles * row_tiles), (unsigned)((ns + LOO_FOLDS - 1) / LOO_FOLDS)), LOO_THREADS, 0, h->stream>>>(
+            h->Ttot.as<T>(), h->loo_ops.as<double>(), ld, h->K, h->M, col_tiles, ns, offs, q.epi.fs + s0, R, h->flags & 15u, want,
+            q.epi.out_xx ? q.epi.out_xx + (size_t)s0 * q.epi.xx_stride : nullptr, q.epi.xx_pitch, q.epi.xx_stride,
+            q.epi.out_xy ? q.epi.out_xy + (size_t)s0 * q.epi.xy_stride : nullptr, q.epi.xy_pitch, q.epi.xy_stride);
+        h->launches += 2;
+      }
+      h->launches--;
     } else {
       k_small_folds<T><<<grid, STHREADS, 0, h->stream>>>(q);
     }

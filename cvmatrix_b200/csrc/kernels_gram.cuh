@@ -1064,4 +1064,145 @@ __global__ void __launch_bounds__(LOO_THREADS, 2) k_loo_tiles(const T* __restric
 #undef LOO_JC
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Leave-few-out (2 .. SMALL_MAX_ROWS validation rows per fold), streaming form: one operand row v_r = rn(sqrt(w_r) z_r)
+// PER validation row, the downdate accumulated on its own in float64 and the epilogue of gram_epilogue:
+//   G_ij = sum_r v_ri v_rj ;  A = rn(T_ij - G_ij) ;  A = rn(A - rn(sw rn(m_i m_j))) ;  A = rn(A (r_i r_j))
+// n FMAs + 6 operations per element instead of the exact form's rounded products and IEEE division (k_small_folds,
+// ~100 instructions per element).  (Folding the centring into the FMA chain, as the one-row kernel does, was measured
+// against the golden fixtures: on data whose mean dwarfs its spread the error is relative to T, 1e-12 of the result.)
+// Every product is symmetric in (i, j) and the FMA chain runs over r in the same order for (i, j) and (j, i): XTX is
+// exactly symmetric.  Operand rows per fold: [mcol | r | mrow | v_0 .. v_{R-1}] x ld float64 (mcol / mrow: the mean where
+// the flags centre that side, else 0), R = the longest fold of the launch.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_few_operands(const T* __restrict__ Z, const T* __restrict__ w, int64_t ld, int64_t K, int64_t M,
+                                                      const int64_t* __restrict__ offs, const int64_t* __restrict__ indices,
+                                                      const T* __restrict__ stats, const FoldScalars* __restrict__ fs, uint32_t flags,
+                                                      int R, double* __restrict__ opnd) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t f = blockIdx.x;
+  if (c >= ld) return;
+  double* o = opnd + (size_t)f * (3 + R) * ld;
+  const int64_t beg = offs[f];
+  const int n = (int)(offs[f + 1] - beg);
+  if (c >= K + M) {
+    o[c] = 0.0; o[ld + c] = 1.0; o[2 * ld + c] = 0.0;
+    for (int r = 0; r < n; ++r) o[(size_t)(3 + r) * ld + c] = 0.0;
+    return;
+  }
+  const bool cX = flags & 1, cY = flags & 2, sX = flags & 4, sY = flags & 8;
+  const bool isX = c < K;
+  const double mean = (double)stats[(size_t)f * 2 * ld + c], sd = (double)stats[(size_t)f * 2 * ld + ld + c];
+  o[c] = (isX ? cX : (cX || cY)) ? mean : 0.0;               // column side
+  o[ld + c] = (isX ? sX : sY) ? __ddiv_rn(1.0, sd) : 1.0;
+  o[2 * ld + c] = (isX && (cX || cY)) ? mean : 0.0;          // row side (X columns only)
+  for (int r = 0; r < n; ++r) {
+    const int64_t row = indices[beg + r];
+    o[(size_t)(3 + r) * ld + c] = __dmul_rn(__dsqrt_rn((double)w[row]), (double)Z[row * ld + c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LOO_THREADS, 2) k_few_tiles(const T* __restrict__ Ttot, const double* __restrict__ opnd, int64_t ld, int64_t K,
+                                                              int64_t M, int col_tiles, int64_t nfolds, const int64_t* __restrict__ offs,
+                                                              const FoldScalars* __restrict__ fs, int R, uint32_t flags, uint32_t want,
+                                                              T* __restrict__ out_xx, int64_t xx_pitch,
+                                                              int64_t xx_stride, T* __restrict__ out_xy, int64_t xy_pitch,
+                                                              int64_t xy_stride) {
+  typedef LooMap<T> Map;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles;
+  const int64_t i0 = (int64_t)rt * LOO_TR + 4 * warp, jt = (int64_t)ct * LOO_TC;
+  const int64_t C = K + M;
+  const int64_t fbeg = (int64_t)blockIdx.y * LOO_FOLDS;
+  const int nf = (int)(min(nfolds, fbeg + LOO_FOLDS) - fbeg);
+  const bool wxx = want & 1, wxy = want & 2;
+  if (i0 >= K || jt >= C) return;
+  if (!((wxx && jt < K) || (wxy && jt + LOO_TC > K))) return;
+  const int nr = (int)min((int64_t)4, K - i0);
+#define LOO_JC(b) (jt + Map::col(lane, (b)))
+  constexpr int VEC = 16 / sizeof(T);
+  const bool aligned = wxx && (xx_pitch % VEC == 0) && (xx_stride % VEC == 0) && (reinterpret_cast<uintptr_t>(out_xx) % 16 == 0);
+  const bool fast1 = aligned && LOO_JC(Map::FIRST - 1) < K;
+  const bool fast2 = aligned && LOO_JC(3) < K;
+  const bool fast = fast1 && (Map::FIRST == 4 || fast2 || LOO_JC(2) >= C);
+
+  T tt[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) tt[a][b] = __ldg(Ttot + min(i0 + a, K - 1) * ld + min(LOO_JC(b), ld - 1));
+  // numpy SKIPS the centring of a block the flags do not centre (XTX iff center_X, XTY iff center_X or center_Y): a mean
+  // that is NaN there (a fold that holds every row) must not reach the result through 0 * NaN
+  bool cen[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) cen[b] = (LOO_JC(b) < K) ? (flags & 1) != 0 : (flags & 3) != 0;
+  const size_t fstride = (size_t)(3 + R) * ld;
+  const double* __restrict__ op = opnd + (size_t)fbeg * fstride;
+  const bool in_ld = jt + LOO_TC <= ld;
+  T* oxx = out_xx + (size_t)fbeg * xx_stride + i0 * xx_pitch + jt;
+  T* oxy = out_xy + (size_t)fbeg * xy_stride + i0 * xy_pitch;
+  auto load_cols = [&](const double* row, double (&v)[4]) {   // the lane's four columns of an operand row
+    if (in_ld) { Map::load(row + jt, lane, v); return; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v[b] = __ldg(row + min(LOO_JC(b), ld - 1));
+  };
+
+#pragma unroll 1
+  for (int f = 0; f < nf; ++f) {
+    const int n = (int)(offs[fbeg + f + 1] - offs[fbeg + f]);
+    const T sw = (T)fs[fbeg + f].sw;
+    double g[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) g[a][b] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < n; ++r) {
+      const double* vr = op + (size_t)(3 + r) * ld;
+      double vj[4];
+      Dbl4 vi;
+      load_cols(vr, vj); vi.load(vr + i0);                          // the row side is warp-uniform (i0 + 3 < ld)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g[a][b] = fma(vi.v[a], vj[b], g[a][b]);
+    }
+    double mj[4], rj[4];
+    Dbl4 mi, ri;
+    load_cols(op, mj); load_cols(op + ld, rj);
+    ri.load(op + ld + i0); mi.load(op + 2 * ld + i0);
+    double o[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        T v = Rn<T>::sub(tt[a][b], (T)g[a][b]);
+        if (cen[b]) v = Rn<T>::sub(v, Rn<T>::mul(sw, Rn<T>::mul((T)mi.v[a], (T)mj[b])));
+        o[a][b] = __dmul_rn((double)v, __dmul_rn(ri.v[a], rj[b]));
+      }
+    if (fast) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a < nr) Map::store(oxx + a * xx_pitch, lane, o[a], fast2);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a >= nr) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int64_t jj = LOO_JC(b);
+          if (jj < K) { if (wxx) oxx[a * xx_pitch + (jj - jt)] = (T)o[a][b]; }
+          else if (jj < C && wxy) oxy[a * xy_pitch + (jj - K)] = (T)o[a][b];
+        }
+      }
+    }
+    op += fstride;
+    oxx += xx_stride;
+    oxy += xy_stride;
+  }
+#undef LOO_JC
+}
+
 }  // namespace cvmx

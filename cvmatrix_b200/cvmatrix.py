@@ -599,8 +599,8 @@ class CVMatrix:
         _lib.check(self._lib.cvmx_set_scan_mode(self._h, int(mode)), self._h)
 
     def set_loo_mode(self, mode: int) -> None:
-        """Leave-one-out batches (include/cvmx.h, cvmx_set_loo_mode): 0 (default) streaming form, matrices within
-        ~1e-15 of the reference; 1 exact form, matrices bit-identical to the reference for one-row folds."""
+        """Leave-one-out / leave-few-out batches (include/cvmx.h, cvmx_set_loo_mode): 0 (default) streaming form, matrices
+        within ~1e-15 of the reference; 1 exact form, matrices bit-identical to the reference for one-row folds."""
         _lib.check(self._lib.cvmx_set_loo_mode(self._h, int(mode)), self._h)
 
     @property

@@ -297,12 +297,12 @@ int64_t cvmx_ld(const cvmx_t* h);
 int32_t cvmx_set_scan_mode(cvmx_t* h, int32_t mode);
 int64_t cvmx_scan_launch_count(const cvmx_t* h);
 
-/* Leave-one-out batches (every fold of a cvmx_training_batch range holds exactly one row; the rank-1 downdate of
- * cvmatrix/cvmatrix.py:1001-1009 is bound by writing K x (K + M) results).  mode 0 (default): streaming form - per
- * element two FMAs and a multiplication by precomputed reciprocal standard deviations, matrices within ~1e-15
- * (relative Frobenius) of the reference and exactly symmetric; mode 1: exact form - numpy's operation order with IEEE
- * division, matrices bit-identical to the reference for one-row folds.  Statistics are bit-identical in both.
- * Also settable with the environment variable CVMX_LOO_EXACT=1 at cvmx_create. */
+/* Leave-one-out and leave-few-out batches (every fold of a cvmx_training_batch range holds at most 16 rows; the rank-n
+ * downdate of cvmatrix/cvmatrix.py:1001-1009 is bound by writing K x (K + M) results).  mode 0 (default): streaming
+ * form - operand rows prepared once per fold, per element a few FMAs and a multiplication by precomputed reciprocal
+ * standard deviations, matrices within ~1e-15 (relative Frobenius) of the reference and exactly symmetric; mode 1: exact
+ * form - numpy's operation order with IEEE division, matrices bit-identical to the reference for one-row folds.
+ * Statistics are bit-identical in both.  Also settable with the environment variable CVMX_LOO_EXACT=1 at cvmx_create. */
 int32_t cvmx_set_loo_mode(cvmx_t* h, int32_t mode);
 
 #ifdef __cplusplus
