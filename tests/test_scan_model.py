@@ -17,14 +17,17 @@ def _from_bits(b):
     return np.uint64(b).view(np.float64)
 
 
-def scan_sum(x, L=64, s0=0.0, counts=None):
+def scan_sum(x, L=64, s0=0.0, counts=None, p_start=None, tot_start=0.0):
+    """s0: the exact chain value before x[0] (pass 4).  p_start / tot_start: what pass 2 uses for it - the same value in the
+    plain scan; in the decoupled slab chain (cvmx_slab_scan_local / _prepare) only an APPROXIMATION of it and the sum of
+    magnitudes of everything before, because the exact chains of the earlier slabs are not known yet."""
     n = len(x)
     S = (n + L - 1) // L
     segS = [np.sum(x[j * L:(j + 1) * L]) for j in range(S)]            # pass 1 (any order)
     segA = [np.sum(np.abs(x[j * L:(j + 1) * L])) for j in range(S)]
     B0 = [0.0] * S
     ident = [False] * S
-    P, tot = np.float64(s0), np.float64(0.0)
+    P, tot = np.float64(s0 if p_start is None else p_start), np.float64(tot_start)
     for j in range(S):                                                  # pass 2
         A1 = segA[j] * (1 + 2.0 ** -20)
         margin = 2.0 ** -24 * tot + 2.0 ** -40 * abs(P)
@@ -111,3 +114,28 @@ def test_scan_model_is_bit_identical_to_the_sequential_chain(L):
             nfast, nseg = counts[0]
             if expect_fast and len(x) >= 20_000:
                 assert nfast >= 0.75 * nseg, (name, L, nfast, nseg)   # the scan actually carries these cases
+
+
+@pytest.mark.parametrize("L", [64, 256])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_decoupled_slab_chain_model(L, world):
+    """Row slabs (cvmx_slab_scan_local / _prepare): every slab runs passes 1 - 3 from the SUM OF THE EARLIER SLABS' pass-1
+    totals (numpy's pairwise sums here: a different order than the chain, so only approximately the chain's value) and the
+    sum of their magnitudes; pass 4 alone continues the exact chain.  The result must still be the sequential chain's, bit
+    for bit - a wrong approximation may only cost slow segments."""
+    with np.errstate(all="ignore"):
+        for name, x, s0, _ in _cases():
+            x = np.asarray(x, dtype=np.float64)
+            if len(x) < 4 * world:
+                continue
+            cuts = [len(x) * r // world for r in range(world + 1)]
+            slabs = [x[cuts[r]:cuts[r + 1]] for r in range(world)]
+            approx = [np.sum(sl) for sl in slabs]                       # pass 1b of every slab, "all-gathered"
+            mags = [np.sum(np.abs(sl)) for sl in slabs]
+            carry = np.float64(s0)
+            for r, sl in enumerate(slabs):
+                p_start = np.float64(s0) + np.sum(approx[:r]) if r else np.float64(s0)
+                tot_start = np.sum(mags[:r]) + (abs(s0) if r else 0.0)
+                carry = scan_sum(sl, L, carry, p_start=p_start, tot_start=tot_start)
+            want = chain_sum(x, s0)
+            assert (_bits(want) == _bits(carry)) or (want != want and carry != carry), (name, L, world, want, carry)
